@@ -1,0 +1,102 @@
+"""ctypes binding of libdpr.so - the same symbols a Julia `ccall` layer binds (include/dpr.h).
+
+There is no CPU fallback: if the library is missing it is built with nvcc; if that fails, or no sm_100 device is
+present at call time, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdpr.so")
+
+# every symbol include/dpr.h declares (tests/test_abi.py checks the header against this list and the .so)
+SYMBOLS = [
+    "dpr_version", "dpr_status_string", "dpr_last_error_message", "dpr_workspace_bytes",
+    "dpr_raster_forward_f32", "dpr_raster_forward_f64", "dpr_raster_pullback_f32", "dpr_raster_pullback_f64",
+    "dpr_raster_forward_host_f32", "dpr_raster_forward_host_f64", "dpr_raster_pullback_host_f32",
+    "dpr_raster_pullback_host_f64", "dpr_host_alloc", "dpr_host_free", "dpr_host_release",
+    "dpr_set_option", "dpr_get_option", "dpr_kernel_launch_count", "dpr_last_path",
+]
+
+OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK = range(5)
+OP_FORWARD, OP_PULLBACK = 0, 1
+
+_lib = None
+
+
+class DprError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"libdpr status {status}: {message}")
+        self.status = status
+
+
+def load() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    c_i, c_i64, c_p, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
+    lib.dpr_version.restype = c_i
+    lib.dpr_status_string.restype = ctypes.c_char_p
+    lib.dpr_status_string.argtypes = [c_i]
+    lib.dpr_last_error_message.restype = ctypes.c_char_p
+    lib.dpr_workspace_bytes.restype = c_sz
+    lib.dpr_workspace_bytes.argtypes = [c_i, c_i, c_i, c_p, c_i64, c_i64, c_i]
+    head = [c_i, c_i, c_p, c_i64, c_i64]
+    for suf in ("f32", "f64"):
+        f = getattr(lib, f"dpr_raster_forward_{suf}")
+        f.restype = c_i
+        f.argtypes = head + [c_p] * 7 + [c_p, c_sz, c_p]
+        f = getattr(lib, f"dpr_raster_pullback_{suf}")
+        f.restype = c_i
+        f.argtypes = head + [c_p] * 12 + [c_p, c_sz, c_p]
+        f = getattr(lib, f"dpr_raster_forward_host_{suf}")
+        f.restype = c_i
+        f.argtypes = head + [c_p] * 7
+        f = getattr(lib, f"dpr_raster_pullback_host_{suf}")
+        f.restype = c_i
+        f.argtypes = head + [c_p] * 12
+    lib.dpr_host_alloc.restype = c_i
+    lib.dpr_host_alloc.argtypes = [ctypes.POINTER(c_p), c_sz]
+    lib.dpr_host_free.restype = c_i
+    lib.dpr_host_free.argtypes = [c_p]
+    lib.dpr_host_release.restype = c_i
+    lib.dpr_set_option.restype = c_i
+    lib.dpr_set_option.argtypes = [c_i, c_i64]
+    lib.dpr_get_option.restype = c_i64
+    lib.dpr_get_option.argtypes = [c_i]
+    lib.dpr_kernel_launch_count.restype = c_i64
+    lib.dpr_last_path.restype = ctypes.c_char_p
+    lib.dpr_last_path.argtypes = [c_i]
+    _lib = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        lib = load()
+        msg = lib.dpr_status_string(status).decode()
+        detail = lib.dpr_last_error_message().decode()
+        raise DprError(status, msg + (f" [{detail}]" if detail else ""))
+
+
+def set_option(option: int, value: int) -> None:
+    check(load().dpr_set_option(option, value))
+
+
+def get_option(option: int) -> int:
+    return int(load().dpr_get_option(option))
+
+
+def kernel_launch_count() -> int:
+    return int(load().dpr_kernel_launch_count())
+
+
+def last_path(op: int) -> str:
+    return load().dpr_last_path(op).decode()

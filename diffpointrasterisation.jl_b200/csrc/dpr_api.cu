@@ -1,0 +1,469 @@
+// dpr_api.cu - the C ABI of libdpr.so (include/dpr.h): validation, dispatch, options, host-buffer entry points.
+// No torch types, no C++ types in the signatures; never throws; there is NO CPU fallback.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "dpr_internal.h"
+
+namespace dpr {
+
+static Tuning g_tuning;
+static std::atomic<int64_t> g_launches{0};
+static thread_local char tl_error[512] = "";
+static thread_local const char* tl_path[2] = {"none", "none"};
+
+const Tuning& tuning() { return g_tuning; }
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+void set_last_path(int op, const char* name) { if (op >= 0 && op < 2) tl_path[op] = name; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(tl_error, sizeof(tl_error), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
+    cudaGetLastError();  // clear the sticky-free error state
+    return DPR_ERR_CUDA;
+}
+
+// per-device attribute cache (the only global mutable state besides options and the host staging arenas)
+static std::mutex g_dev_mutex;
+static DeviceInfo g_dev_cache[64];
+
+int current_device_info(DeviceInfo& info) {
+    int dev = -1;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) { cuda_fail(e, "cudaGetDevice"); return DPR_ERR_NO_DEVICE; }
+    if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(g_dev_mutex);
+    DeviceInfo& c = g_dev_cache[dev];
+    if (c.device != dev) {
+        DeviceInfo d;
+        d.device = dev;
+        DPR_CUDA_TRY(cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        DPR_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        DPR_CUDA_TRY(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+        DPR_CUDA_TRY(cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        if (d.cc_major != 10) {
+            snprintf(tl_error, sizeof(tl_error), "device %d is sm_%d%d; libdpr.so holds sm_100a kernels only", dev,
+                     d.cc_major, d.cc_minor);
+            return DPR_ERR_NO_DEVICE;
+        }
+        c = d;
+    }
+    info = c;
+    return DPR_OK;
+}
+
+static int check_dims(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B) {
+    if (!grid) return DPR_ERR_NULL_POINTER;
+    if (!((n_in == 2 && n_out == 2) || (n_in == 3 && n_out == 2) || (n_in == 3 && n_out == 3))) return DPR_ERR_UNSUPPORTED;
+    if (P < 0 || B < 0) return DPR_ERR_BAD_DIMS;
+    int64_t cells = 1;
+    for (int k = 0; k < n_out; ++k) {
+        if (grid[k] < 1 || grid[k] > (int64_t)1 << 20) return DPR_ERR_BAD_DIMS;
+        cells *= grid[k];
+        if (cells > (int64_t)1 << 40) return DPR_ERR_BAD_DIMS;
+    }
+    if (B > 0 && cells > ((int64_t)1 << 46) / B) return DPR_ERR_BAD_DIMS;
+    if (P > (int64_t)1 << 40) return DPR_ERR_BAD_DIMS;
+    return DPR_OK;
+}
+
+template <typename T>
+static int forward_entry(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const T* points,
+                         const T* rotation, const T* translation, const T* background, const T* out_weight,
+                         const T* point_weight, T* out, void* workspace, size_t workspace_bytes, dpr_stream_t stream) {
+    int rc = check_dims(n_in, n_out, grid, P, B);
+    if (rc != DPR_OK) return rc;
+    if ((P > 0 && !points) || (B > 0 && (!rotation || !translation || !out))) return DPR_ERR_NULL_POINTER;
+    if (workspace_bytes < forward_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
+    DeviceInfo dev;
+    rc = current_device_info(dev);
+    if (rc != DPR_OK) return rc;
+    ForwardArgs<T> a;
+    a.n_in = n_in; a.n_out = n_out;
+    for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
+    a.P = P; a.B = B;
+    a.points = points; a.rotation = rotation; a.translation = translation;
+    a.background = background; a.out_weight = out_weight; a.point_weight = point_weight;
+    a.out = out; a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.stream = static_cast<cudaStream_t>(stream);
+    if (B == 0) return DPR_OK;
+    return forward_dispatch<T>(a, dev);
+}
+
+template <typename T>
+static int pullback_entry(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const T* ds_dout,
+                          const T* points, const T* rotation, const T* translation, const T* out_weight,
+                          const T* point_weight, T* d_points, T* d_rotation, T* d_translation, T* d_background,
+                          T* d_out_weight, T* d_point_weight, void* workspace, size_t workspace_bytes,
+                          dpr_stream_t stream) {
+    int rc = check_dims(n_in, n_out, grid, P, B);
+    if (rc != DPR_OK) return rc;
+    if ((P > 0 && (!points || !d_points)) || (B > 0 && (!rotation || !translation || !ds_dout || !d_rotation || !d_translation)))
+        return DPR_ERR_NULL_POINTER;
+    if (workspace_bytes < pullback_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
+    DeviceInfo dev;
+    rc = current_device_info(dev);
+    if (rc != DPR_OK) return rc;
+    PullbackArgs<T> a;
+    a.n_in = n_in; a.n_out = n_out;
+    for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
+    a.P = P; a.B = B;
+    a.ds_dout = ds_dout; a.points = points; a.rotation = rotation; a.translation = translation;
+    a.out_weight = out_weight; a.point_weight = point_weight;
+    a.d_points = d_points; a.d_rotation = d_rotation; a.d_translation = d_translation;
+    a.d_background = d_background; a.d_out_weight = d_out_weight; a.d_point_weight = d_point_weight;
+    a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.stream = static_cast<cudaStream_t>(stream);
+    return pullback_dispatch<T>(a, dev);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host-buffer entry points: pose chunks are pipelined through a per-device staging arena on NSTREAM streams so
+// that the H2D copy of chunk i+1, the kernels of chunk i and the D2H copy of chunk i-1 overlap.
+// ---------------------------------------------------------------------------------------------------------
+static constexpr int NSTREAM = 3;
+
+struct HostArena {
+    int device = -1;
+    cudaStream_t streams[NSTREAM] = {nullptr, nullptr, nullptr};
+    cudaEvent_t shared_ready = nullptr;
+    void* shared = nullptr;   size_t shared_bytes = 0;    // points, point_weight, pose-summed gradients
+    void* slot[NSTREAM] = {nullptr, nullptr, nullptr};
+    size_t slot_bytes = 0;
+};
+static std::mutex g_arena_mutex;
+static HostArena g_arena[64];
+
+static int arena_get(HostArena*& out) {
+    int dev = -1;
+    DPR_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
+    HostArena& a = g_arena[dev];
+    if (a.device != dev) {
+        for (int i = 0; i < NSTREAM; ++i) DPR_CUDA_TRY(cudaStreamCreateWithFlags(&a.streams[i], cudaStreamNonBlocking));
+        DPR_CUDA_TRY(cudaEventCreateWithFlags(&a.shared_ready, cudaEventDisableTiming));
+        a.device = dev;
+    }
+    out = &a;
+    return DPR_OK;
+}
+static int arena_reserve(void*& ptr, size_t& have, size_t want) {
+    if (want <= have) return DPR_OK;
+    if (ptr) DPR_CUDA_TRY(cudaFree(ptr));
+    ptr = nullptr; have = 0;
+    want = (want + 4095) / 4096 * 4096;
+    DPR_CUDA_TRY(cudaMalloc(&ptr, want));
+    have = want;
+    return DPR_OK;
+}
+static size_t align256(size_t n) { return (n + 255) / 256 * 256; }
+
+// poses per chunk: ~64 MB of image data per slot keeps copies long enough to reach PCIe rate
+static int64_t host_chunk_poses(int64_t cells, int64_t B, size_t sizeof_T) {
+    const int64_t target = (int64_t)64 << 20;
+    int64_t n = target / (cells * (int64_t)sizeof_T);
+    if (n < 1) n = 1;
+    if (n > B) n = B;
+    return n;
+}
+
+template <typename T>
+static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const T* points,
+                        const T* rotation, const T* translation, const T* background, const T* out_weight,
+                        const T* point_weight, T* out) {
+    int rc = check_dims(n_in, n_out, grid, P, B);
+    if (rc != DPR_OK) return rc;
+    if ((P > 0 && !points) || (B > 0 && (!rotation || !translation || !out))) return DPR_ERR_NULL_POINTER;
+    if (B == 0) return DPR_OK;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    HostArena* ar = nullptr;
+    rc = arena_get(ar);
+    if (rc != DPR_OK) return rc;
+    int64_t cells = 1;
+    for (int k = 0; k < n_out; ++k) cells *= grid[k];
+    const int64_t cb = host_chunk_poses(cells, B, sizeof(T));
+    const size_t pts_bytes = align256(sizeof(T) * (size_t)(P * n_in)), pw_bytes = align256(sizeof(T) * (size_t)P);
+    rc = arena_reserve(ar->shared, ar->shared_bytes, pts_bytes + pw_bytes + 256);
+    if (rc != DPR_OK) return rc;
+    const size_t rot_b = align256(sizeof(T) * (size_t)(cb * n_out * n_in)), tr_b = align256(sizeof(T) * (size_t)(cb * n_out));
+    const size_t vec_b = align256(sizeof(T) * (size_t)cb), img_b = align256(sizeof(T) * (size_t)(cb * cells));
+    const size_t need = rot_b + tr_b + 2 * vec_b + img_b;
+    if (need > ar->slot_bytes) {
+        size_t have = 0;
+        for (int i = 0; i < NSTREAM; ++i) { have = ar->slot_bytes; rc = arena_reserve(ar->slot[i], have, need); if (rc != DPR_OK) return rc; }
+        ar->slot_bytes = have;
+    }
+    T* d_points = static_cast<T*>(ar->shared);
+    T* d_pw = reinterpret_cast<T*>(static_cast<char*>(ar->shared) + pts_bytes);
+    cudaStream_t s0 = ar->streams[0];
+    if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_points, points, sizeof(T) * (size_t)(P * n_in), cudaMemcpyHostToDevice, s0));
+    if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
+    DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
+    int64_t chunk = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += cb, ++chunk) {
+        const int64_t nb = (b0 + cb < B) ? cb : B - b0;
+        const int si = (int)(chunk % NSTREAM);
+        cudaStream_t st = ar->streams[si];
+        char* base = static_cast<char*>(ar->slot[si]);
+        T* d_rot = reinterpret_cast<T*>(base);
+        T* d_tr = reinterpret_cast<T*>(base + rot_b);
+        T* d_bg = reinterpret_cast<T*>(base + rot_b + tr_b);
+        T* d_ow = reinterpret_cast<T*>(base + rot_b + tr_b + vec_b);
+        T* d_out = reinterpret_cast<T*>(base + rot_b + tr_b + 2 * vec_b);
+        DPR_CUDA_TRY(cudaStreamWaitEvent(st, ar->shared_ready, 0));
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_rot, rotation + b0 * n_out * n_in, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyHostToDevice, st));
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_tr, translation + b0 * n_out, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyHostToDevice, st));
+        if (background) DPR_CUDA_TRY(cudaMemcpyAsync(d_bg, background + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        rc = forward_entry<T>(n_in, n_out, grid, P, nb, d_points, d_rot, d_tr, background ? d_bg : nullptr,
+                              out_weight ? d_ow : nullptr, point_weight ? d_pw : nullptr, d_out, nullptr, 0, st);
+        if (rc != DPR_OK) break;
+        DPR_CUDA_TRY(cudaMemcpyAsync(out + b0 * cells, d_out, sizeof(T) * (size_t)(nb * cells), cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < NSTREAM; ++i) {
+        cudaError_t e = cudaStreamSynchronize(ar->streams[i]);
+        if (e != cudaSuccess && rc == DPR_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    return rc;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) accumulate_kernel(T* __restrict__ dst, const T* __restrict__ src, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] += src[i];
+}
+
+template <typename T>
+static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const T* ds_dout,
+                         const T* points, const T* rotation, const T* translation, const T* out_weight,
+                         const T* point_weight, T* h_dp, T* h_drot, T* h_dtr, T* h_dbg, T* h_dow, T* h_dpw) {
+    int rc = check_dims(n_in, n_out, grid, P, B);
+    if (rc != DPR_OK) return rc;
+    if ((P > 0 && (!points || !h_dp)) || (B > 0 && (!rotation || !translation || !ds_dout || !h_drot || !h_dtr)))
+        return DPR_ERR_NULL_POINTER;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    HostArena* ar = nullptr;
+    rc = arena_get(ar);
+    if (rc != DPR_OK) return rc;
+    int64_t cells = 1;
+    for (int k = 0; k < n_out; ++k) cells *= grid[k];
+    const int64_t cb = B > 0 ? host_chunk_poses(cells, B, sizeof(T)) : 1;
+    // shared: points, point_weight, total d_points (+d_point_weight), and one partial buffer per stream
+    const size_t pts_bytes = align256(sizeof(T) * (size_t)(P * n_in)), pw_bytes = align256(sizeof(T) * (size_t)P);
+    const size_t grad_bytes = pts_bytes + pw_bytes;
+    rc = arena_reserve(ar->shared, ar->shared_bytes, pts_bytes + pw_bytes + grad_bytes * (1 + NSTREAM) + 256);
+    if (rc != DPR_OK) return rc;
+    const size_t rot_b = align256(sizeof(T) * (size_t)(cb * n_out * n_in)), tr_b = align256(sizeof(T) * (size_t)(cb * n_out));
+    const size_t vec_b = align256(sizeof(T) * (size_t)cb), img_b = align256(sizeof(T) * (size_t)(cb * cells));
+    const size_t need = 2 * rot_b + 2 * tr_b + 3 * vec_b + img_b;
+    if (need > ar->slot_bytes) {
+        size_t have = 0;
+        for (int i = 0; i < NSTREAM; ++i) { have = ar->slot_bytes; rc = arena_reserve(ar->slot[i], have, need); if (rc != DPR_OK) return rc; }
+        ar->slot_bytes = have;
+    }
+    char* sh = static_cast<char*>(ar->shared);
+    T* d_points = reinterpret_cast<T*>(sh);
+    T* d_pw = reinterpret_cast<T*>(sh + pts_bytes);
+    T* tot_dp = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes);
+    T* tot_dpw = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + pts_bytes);
+    cudaStream_t s0 = ar->streams[0];
+    if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_points, points, sizeof(T) * (size_t)(P * n_in), cudaMemcpyHostToDevice, s0));
+    if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
+    DPR_CUDA_TRY(cudaMemsetAsync(tot_dp, 0, grad_bytes, s0));
+    DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
+    int64_t chunk = 0;
+    cudaEvent_t done[NSTREAM] = {nullptr, nullptr, nullptr};
+    for (int64_t b0 = 0; b0 < B && rc == DPR_OK; b0 += cb, ++chunk) {
+        const int64_t nb = (b0 + cb < B) ? cb : B - b0;
+        const int si = (int)(chunk % NSTREAM);
+        cudaStream_t st = ar->streams[si];
+        char* base = static_cast<char*>(ar->slot[si]);
+        T* d_rot = reinterpret_cast<T*>(base);
+        T* d_tr = reinterpret_cast<T*>(base + rot_b);
+        T* d_ow = reinterpret_cast<T*>(base + rot_b + tr_b);
+        T* g_rot = reinterpret_cast<T*>(base + rot_b + tr_b + vec_b);
+        T* g_tr = reinterpret_cast<T*>(base + 2 * rot_b + tr_b + vec_b);
+        T* g_bg = reinterpret_cast<T*>(base + 2 * rot_b + 2 * tr_b + vec_b);
+        T* g_ow = reinterpret_cast<T*>(base + 2 * rot_b + 2 * tr_b + 2 * vec_b);
+        T* d_img = reinterpret_cast<T*>(base + 2 * rot_b + 2 * tr_b + 3 * vec_b);
+        T* part_dp = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + grad_bytes * (1 + si));
+        T* part_dpw = reinterpret_cast<T*>(reinterpret_cast<char*>(part_dp) + pts_bytes);
+        DPR_CUDA_TRY(cudaStreamWaitEvent(st, ar->shared_ready, 0));
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_img, ds_dout + b0 * cells, sizeof(T) * (size_t)(nb * cells), cudaMemcpyHostToDevice, st));
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_rot, rotation + b0 * n_out * n_in, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyHostToDevice, st));
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_tr, translation + b0 * n_out, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyHostToDevice, st));
+        if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
+        rc = pullback_entry<T>(n_in, n_out, grid, P, nb, d_img, d_points, d_rot, d_tr, out_weight ? d_ow : nullptr,
+                               point_weight ? d_pw : nullptr, part_dp, g_rot, g_tr, h_dbg ? g_bg : nullptr,
+                               h_dow ? g_ow : nullptr, h_dpw ? part_dpw : nullptr, nullptr, 0, st);
+        if (rc != DPR_OK) break;
+        DPR_CUDA_TRY(cudaMemcpyAsync(h_drot + b0 * n_out * n_in, g_rot, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyDeviceToHost, st));
+        DPR_CUDA_TRY(cudaMemcpyAsync(h_dtr + b0 * n_out, g_tr, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyDeviceToHost, st));
+        if (h_dbg) DPR_CUDA_TRY(cudaMemcpyAsync(h_dbg + b0, g_bg, sizeof(T) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        if (h_dow) DPR_CUDA_TRY(cudaMemcpyAsync(h_dow + b0, g_ow, sizeof(T) * (size_t)nb, cudaMemcpyDeviceToHost, st));
+        // fold this chunk's pose-sum into the total on stream 0 (serialises the adds, keeps them race-free)
+        if (!done[si]) DPR_CUDA_TRY(cudaEventCreateWithFlags(&done[si], cudaEventDisableTiming));
+        DPR_CUDA_TRY(cudaEventRecord(done[si], st));
+        DPR_CUDA_TRY(cudaStreamWaitEvent(s0, done[si], 0));
+        const int64_t n_acc = (int64_t)(grad_bytes / sizeof(T));
+        int64_t blocks = (n_acc + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (n_acc > 0) {
+            accumulate_kernel<T><<<(unsigned)blocks, 256, 0, s0>>>(tot_dp, part_dp, n_acc);
+            count_launches(1);
+        }
+        // the slot's partial buffer may only be reused after the fold: make the slot's stream wait for it
+        DPR_CUDA_TRY(cudaEventRecord(done[si], s0));
+        DPR_CUDA_TRY(cudaStreamWaitEvent(st, done[si], 0));
+    }
+    for (int i = 1; i < NSTREAM; ++i) {
+        cudaError_t e = cudaStreamSynchronize(ar->streams[i]);
+        if (e != cudaSuccess && rc == DPR_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    }
+    if (rc == DPR_OK) {
+        if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(h_dp, tot_dp, sizeof(T) * (size_t)(P * n_in), cudaMemcpyDeviceToHost, s0));
+        if (h_dpw && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(h_dpw, tot_dpw, sizeof(T) * (size_t)P, cudaMemcpyDeviceToHost, s0));
+    }
+    cudaError_t e = cudaStreamSynchronize(s0);
+    if (e != cudaSuccess && rc == DPR_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
+    for (int i = 0; i < NSTREAM; ++i) if (done[i]) cudaEventDestroy(done[i]);
+    return rc;
+}
+
+}  // namespace dpr
+
+using namespace dpr;
+
+extern "C" {
+
+int dpr_version(void) { return 100; }
+
+const char* dpr_status_string(int status) {
+    switch (status) {
+        case DPR_OK: return "ok";
+        case DPR_ERR_BAD_DIMS: return "bad dimensions (negative size, grid extent < 1, or size overflow)";
+        case DPR_ERR_UNSUPPORTED: return "unsupported (N_in, N_out) or element type; supported: (2,2), (3,2), (3,3) in f32/f64";
+        case DPR_ERR_NULL_POINTER: return "a required pointer is NULL";
+        case DPR_ERR_WORKSPACE: return "workspace smaller than dpr_workspace_bytes()";
+        case DPR_ERR_CUDA: return "CUDA runtime error (see dpr_last_error_message)";
+        case DPR_ERR_NO_DEVICE: return "no usable sm_100 CUDA device; libdpr has no CPU fallback";
+        case DPR_ERR_NCCL: return "NCCL error";
+        case DPR_ERR_BAD_OPTION: return "unknown option or bad option value";
+        default: return "unknown status";
+    }
+}
+
+const char* dpr_last_error_message(void) { return tl_error; }
+
+size_t dpr_workspace_bytes(int op, int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, int sizeof_T) {
+    if (op == DPR_OP_FORWARD) return forward_workspace_bytes(n_in, n_out, grid, P, B, sizeof_T);
+    if (op == DPR_OP_PULLBACK) return pullback_workspace_bytes(n_in, n_out, grid, P, B, sizeof_T);
+    return 0;
+}
+
+int dpr_raster_forward_f32(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const float* points,
+                           const float* rotation, const float* translation, const float* background,
+                           const float* out_weight, const float* point_weight, float* out, void* ws, size_t ws_bytes,
+                           dpr_stream_t stream) {
+    return forward_entry<float>(n_in, n_out, grid, P, B, points, rotation, translation, background, out_weight, point_weight, out, ws, ws_bytes, stream);
+}
+int dpr_raster_forward_f64(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const double* points,
+                           const double* rotation, const double* translation, const double* background,
+                           const double* out_weight, const double* point_weight, double* out, void* ws, size_t ws_bytes,
+                           dpr_stream_t stream) {
+    return forward_entry<double>(n_in, n_out, grid, P, B, points, rotation, translation, background, out_weight, point_weight, out, ws, ws_bytes, stream);
+}
+int dpr_raster_pullback_f32(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const float* ds_dout,
+                            const float* points, const float* rotation, const float* translation,
+                            const float* out_weight, const float* point_weight, float* d_points, float* d_rotation,
+                            float* d_translation, float* d_background, float* d_out_weight, float* d_point_weight,
+                            void* ws, size_t ws_bytes, dpr_stream_t stream) {
+    return pullback_entry<float>(n_in, n_out, grid, P, B, ds_dout, points, rotation, translation, out_weight, point_weight,
+                                 d_points, d_rotation, d_translation, d_background, d_out_weight, d_point_weight, ws, ws_bytes, stream);
+}
+int dpr_raster_pullback_f64(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const double* ds_dout,
+                            const double* points, const double* rotation, const double* translation,
+                            const double* out_weight, const double* point_weight, double* d_points, double* d_rotation,
+                            double* d_translation, double* d_background, double* d_out_weight, double* d_point_weight,
+                            void* ws, size_t ws_bytes, dpr_stream_t stream) {
+    return pullback_entry<double>(n_in, n_out, grid, P, B, ds_dout, points, rotation, translation, out_weight, point_weight,
+                                  d_points, d_rotation, d_translation, d_background, d_out_weight, d_point_weight, ws, ws_bytes, stream);
+}
+
+int dpr_raster_forward_host_f32(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const float* points,
+                                const float* rotation, const float* translation, const float* background,
+                                const float* out_weight, const float* point_weight, float* out) {
+    return forward_host<float>(n_in, n_out, grid, P, B, points, rotation, translation, background, out_weight, point_weight, out);
+}
+int dpr_raster_forward_host_f64(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const double* points,
+                                const double* rotation, const double* translation, const double* background,
+                                const double* out_weight, const double* point_weight, double* out) {
+    return forward_host<double>(n_in, n_out, grid, P, B, points, rotation, translation, background, out_weight, point_weight, out);
+}
+int dpr_raster_pullback_host_f32(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const float* ds_dout,
+                                 const float* points, const float* rotation, const float* translation,
+                                 const float* out_weight, const float* point_weight, float* d_points,
+                                 float* d_rotation, float* d_translation, float* d_background, float* d_out_weight,
+                                 float* d_point_weight) {
+    return pullback_host<float>(n_in, n_out, grid, P, B, ds_dout, points, rotation, translation, out_weight, point_weight,
+                                d_points, d_rotation, d_translation, d_background, d_out_weight, d_point_weight);
+}
+int dpr_raster_pullback_host_f64(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const double* ds_dout,
+                                 const double* points, const double* rotation, const double* translation,
+                                 const double* out_weight, const double* point_weight, double* d_points,
+                                 double* d_rotation, double* d_translation, double* d_background, double* d_out_weight,
+                                 double* d_point_weight) {
+    return pullback_host<double>(n_in, n_out, grid, P, B, ds_dout, points, rotation, translation, out_weight, point_weight,
+                                 d_points, d_rotation, d_translation, d_background, d_out_weight, d_point_weight);
+}
+
+int dpr_host_alloc(void** ptr, size_t bytes) {
+    if (!ptr) return DPR_ERR_NULL_POINTER;
+    DPR_CUDA_TRY(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return DPR_OK;
+}
+int dpr_host_free(void* ptr) {
+    if (ptr) DPR_CUDA_TRY(cudaFreeHost(ptr));
+    return DPR_OK;
+}
+int dpr_host_release(void) {
+    int dev = -1;
+    DPR_CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
+    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    HostArena& a = g_arena[dev];
+    if (a.device != dev) return DPR_OK;
+    for (int i = 0; i < NSTREAM; ++i) { if (a.slot[i]) cudaFree(a.slot[i]); a.slot[i] = nullptr; }
+    a.slot_bytes = 0;
+    if (a.shared) cudaFree(a.shared);
+    a.shared = nullptr; a.shared_bytes = 0;
+    return DPR_OK;
+}
+
+int dpr_set_option(int option, int64_t value) {
+    if (value < 0) return DPR_ERR_BAD_OPTION;
+    switch (option) {
+        case DPR_OPT_FORWARD_ALGO: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.forward_algo = value; return DPR_OK;
+        case DPR_OPT_PULLBACK_ALGO: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.pullback_algo = value; return DPR_OK;
+        case DPR_OPT_TILE_SMEM_BYTES: g_tuning.tile_smem_bytes = value; return DPR_OK;
+        case DPR_OPT_POINT_SPLIT: g_tuning.point_split = value; return DPR_OK;
+        case DPR_OPT_POSE_CHUNK: g_tuning.pose_chunk = value; return DPR_OK;
+        default: return DPR_ERR_BAD_OPTION;
+    }
+}
+int64_t dpr_get_option(int option) {
+    switch (option) {
+        case DPR_OPT_FORWARD_ALGO: return g_tuning.forward_algo;
+        case DPR_OPT_PULLBACK_ALGO: return g_tuning.pullback_algo;
+        case DPR_OPT_TILE_SMEM_BYTES: return g_tuning.tile_smem_bytes;
+        case DPR_OPT_POINT_SPLIT: return g_tuning.point_split;
+        case DPR_OPT_POSE_CHUNK: return g_tuning.pose_chunk;
+        default: return -1;
+    }
+}
+int64_t dpr_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* dpr_last_path(int op) { return (op >= 0 && op < 2) ? tl_path[op] : "none"; }
+
+}  // extern "C"

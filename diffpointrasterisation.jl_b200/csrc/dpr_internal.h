@@ -1,0 +1,67 @@
+// dpr_internal.h - host-side declarations shared by the translation units of libdpr.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/dpr.h"
+
+namespace dpr {
+
+struct DeviceInfo {
+    int device = -1;
+    int sm_count = 0;
+    int cc_major = 0, cc_minor = 0;
+    int max_smem_optin = 0;  // bytes of dynamic shared memory one CTA may opt in to
+};
+
+struct Tuning {
+    int64_t forward_algo = 0;
+    int64_t pullback_algo = 0;
+    int64_t tile_smem_bytes = 0;
+    int64_t point_split = 0;
+    int64_t pose_chunk = 0;
+};
+
+const Tuning& tuning();
+int current_device_info(DeviceInfo& info);          // DPR_OK or negative status
+void count_launches(int n);
+void set_last_path(int op, const char* name);
+int cuda_fail(cudaError_t e, const char* what);     // records the message, returns DPR_ERR_CUDA
+
+#define DPR_CUDA_TRY(expr)                                              \
+    do {                                                                \
+        cudaError_t e__ = (expr);                                       \
+        if (e__ != cudaSuccess) return ::dpr::cuda_fail(e__, #expr);    \
+    } while (0)
+
+template <typename T>
+struct ForwardArgs {
+    int n_in, n_out;
+    int64_t grid[3];
+    int64_t P, B;
+    const T *points, *rotation, *translation, *background, *out_weight, *point_weight;
+    T* out;
+    void* workspace;
+    size_t workspace_bytes;
+    cudaStream_t stream;
+};
+
+template <typename T>
+struct PullbackArgs {
+    int n_in, n_out;
+    int64_t grid[3];
+    int64_t P, B;
+    const T *ds_dout, *points, *rotation, *translation, *out_weight, *point_weight;
+    T *d_points, *d_rotation, *d_translation, *d_background, *d_out_weight, *d_point_weight;
+    void* workspace;
+    size_t workspace_bytes;
+    cudaStream_t stream;
+};
+
+template <typename T> int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev);
+template <typename T> int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev);
+size_t forward_workspace_bytes(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, int sizeof_T);
+size_t pullback_workspace_bytes(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, int sizeof_T);
+
+}  // namespace dpr

@@ -1,0 +1,274 @@
+// dpr_pullback.cu - batched pullback of the splat for sm_100a.
+//
+// Replaces the reference's CUDA pullback (ext/DiffPointRasterisationCUDAExt.jl:19-210 kernel, :231-321 driver)
+// and computes the same gradients as the CPU method (src/raster_pullback.jl:2-82 per pose, :85-148 batched):
+// gather ds_dout at the 2^N_out stencil cells of every (point, pose) pair and reduce to
+//   d_points (summed over poses), d_point_weight (summed over poses),
+//   d_rotation, d_translation, d_out_weight (summed over points, per pose), d_background (sum of ds_dout, per pose).
+//
+// Decomposition: a thread OWNS K points and loops over the poses of its CTA's pose chunk, so
+// the pose-sum of d_points / d_point_weight is a register accumulation (one REDG per point and pose chunk, not per
+// splat); the per-pose point-sums are reduced with warp shuffles, combined per CTA in shared memory, and leave the
+// CTA as one REDG per (pose, value).  CTAs are ordered so that neighbours work on the same poses at the same time,
+// which keeps the ds_dout images they gather from resident in L1/L2.
+#include "dpr_common.cuh"
+#include "dpr_internal.h"
+
+namespace dpr {
+
+template <int N_IN, int N_OUT>
+struct PoseGradLayout {
+    // per-pose values reduced over points: d_rotation (N_OUT*N_IN, column-major), d_translation (N_OUT), d_out_weight
+    static constexpr int NV = N_OUT * N_IN + N_OUT + 1;
+};
+
+// Gradient pieces of one (point, pose) pair.  `img` is the pose's ds_dout image.
+//   s      = sum_c W_c G_c                                 (src/raster_pullback.jl:55-58)
+//   gk[n]  = sum_c G_c * sign_n(c) * prod_{m != n} w_m(c)  (src/raster_pullback.jl:60-65, :150-160)
+// Out-of-bounds corners are skipped individually (src/raster_pullback.jl:51).
+template <typename T, int N_OUT, typename Fetch>
+__device__ __forceinline__ void gather_corners(const Grid<T, N_OUT>& grid, const int (&i0)[N_OUT], const T (&dl)[N_OUT],
+                                               Fetch fetch, T& s, T (&gk)[N_OUT]) {
+    T du[N_OUT];
+#pragma unroll
+    for (int k = 0; k < N_OUT; ++k) { du[k] = T(1) - dl[k]; gk[k] = T(0); }
+    s = T(0);
+#pragma unroll
+    for (int c = 0; c < (1 << N_OUT); ++c) {
+        bool inb = true;
+        int64_t off = 0, stride = 1;
+#pragma unroll
+        for (int k = 0; k < N_OUT; ++k) {
+            const int idx = i0[k] + ((c >> k) & 1);
+            inb = inb && idx >= 0 && idx < grid.g[k];
+            off += idx * stride;
+            stride *= grid.g[k];
+        }
+        const T G = inb ? fetch(off) : T(0);
+        s += corner_weight<T, N_OUT>(c, dl, du) * G;
+#pragma unroll
+        for (int n = 0; n < N_OUT; ++n) {
+            T iw = ((c >> n) & 1) ? T(1) : T(-1);
+#pragma unroll
+            for (int m = 0; m < N_OUT; ++m)
+                if (m != n) iw *= ((c >> m) & 1) ? dl[m] : du[m];
+            gk[n] += G * iw;
+        }
+    }
+}
+
+template <typename T, int N_IN, int N_OUT, int K>
+__global__ void __launch_bounds__(256)
+pullback_gather_global_kernel(const T* __restrict__ ds_dout, const T* __restrict__ points,
+                              const T* __restrict__ rotation, const T* __restrict__ translation,
+                              const T* __restrict__ out_weight, const T* __restrict__ point_weight,
+                              T* __restrict__ d_points, T* __restrict__ d_rotation, T* __restrict__ d_translation,
+                              T* __restrict__ d_out_weight, T* __restrict__ d_point_weight, Grid<T, N_OUT> grid,
+                              int64_t P, int64_t B, int point_chunks, int pose_chunk) {
+    constexpr int NV = PoseGradLayout<N_IN, N_OUT>::NV;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* pose_acc = reinterpret_cast<T*>(smem_raw);  // [pose_chunk][NV]
+
+    const int pc = blockIdx.x % point_chunks;
+    const int64_t bc = blockIdx.x / point_chunks;
+    const int64_t b0 = bc * pose_chunk;
+    const int64_t b1 = (b0 + pose_chunk < B) ? b0 + pose_chunk : B;
+    const int n_pose = (int)(b1 - b0);
+    for (int i = threadIdx.x; i < n_pose * NV; i += blockDim.x) pose_acc[i] = T(0);
+    __syncthreads();
+
+    T x[K][N_IN], pw[K], dpt[K][N_IN], dpw[K];
+    bool valid[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int64_t p = ((int64_t)pc * K + k) * blockDim.x + threadIdx.x;
+        valid[k] = p < P;
+        const int64_t pp = valid[k] ? p : 0;
+        load_point(x[k], points, pp);
+        pw[k] = point_weight ? __ldg(point_weight + pp) : T(1);
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) dpt[k][j] = T(0);
+        dpw[k] = T(0);
+    }
+
+    const int lane = threadIdx.x & 31;
+    for (int64_t b = b0; b < b1; ++b) {
+        Pose<T, N_IN, N_OUT> pose;
+        load_pose(pose, rotation, translation, out_weight, b);
+        const T* __restrict__ img = ds_dout + b * grid.cells;
+        T acc[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[v] = T(0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            int i0[N_OUT];
+            T dl[N_OUT];
+            if (!valid[k] || !stencil(x[k], pose, grid, i0, dl)) continue;
+            T s, gk[N_OUT];
+            gather_corners<T, N_OUT>(grid, i0, dl, [&](int64_t off) { return __ldg(img + off); }, s, gk);
+            acc[NV - 1] += s * pw[k];                         // d_out_weight,   src/raster_pullback.jl:57
+            dpw[k] += s * pose.ow;                            // d_point_weight, src/raster_pullback.jl:58
+            const T f = pose.ow * pw[k];                      // factor / G,     src/raster_pullback.jl:60
+            T scaled[N_OUT];
+#pragma unroll
+            for (int n = 0; n < N_OUT; ++n) {
+                scaled[n] = (f * gk[n]) * grid.scale[n];      // src/raster_pullback.jl:67
+                acc[N_OUT * N_IN + n] += scaled[n];           // d_translation,  src/raster_pullback.jl:68
+            }
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) {
+                T d = T(0);
+#pragma unroll
+                for (int n = 0; n < N_OUT; ++n) {
+                    acc[n + j * N_OUT] += scaled[n] * x[k][j];   // d_rotation, src/raster_pullback.jl:69
+                    d += pose.R[n][j] * scaled[n];               // R' * scaled, src/raster_pullback.jl:70
+                }
+                dpt[k][j] += d;                                   // src/raster_pullback.jl:71
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const T r = warp_sum(acc[v]);
+            if (lane == 0 && r != T(0)) atomicAdd(&pose_acc[(int)(b - b0) * NV + v], r);
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (!valid[k]) continue;
+        const int64_t p = ((int64_t)pc * K + k) * blockDim.x + threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) red_add(d_points + p * N_IN + j, dpt[k][j]);
+        if (d_point_weight) red_add(d_point_weight + p, dpw[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pose * NV; i += blockDim.x) {
+        const int bl = i / NV, v = i % NV;
+        const T r = pose_acc[i];
+        const int64_t b = b0 + bl;
+        if (v < N_OUT * N_IN) red_add(d_rotation + b * (N_OUT * N_IN) + v, r);
+        else if (v < N_OUT * N_IN + N_OUT) red_add(d_translation + b * N_OUT + (v - N_OUT * N_IN), r);
+        else if (d_out_weight) red_add(d_out_weight + b, r);
+    }
+}
+
+// d_background[b] = sum(ds_dout[:, b])   (src/raster_pullback.jl:78; ext/DiffPointRasterisationCUDAExt.jl:265-267)
+template <typename T>
+__global__ void __launch_bounds__(256)
+background_sum_kernel(const T* __restrict__ ds_dout, T* __restrict__ d_background, int64_t cells, int segs,
+                      int64_t seg_len) {
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) Pack { T v[VEC]; };
+    const int64_t b = blockIdx.x / segs;
+    const int seg = blockIdx.x % segs;
+    const int64_t lo = (int64_t)seg * seg_len;
+    const int64_t hi = (lo + seg_len < cells) ? lo + seg_len : cells;
+    const T* __restrict__ src = ds_dout + b * cells;
+    T s = T(0);
+    if ((cells % VEC) == 0 && (seg_len % VEC) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) % 16) == 0) {
+        const Pack* __restrict__ v = reinterpret_cast<const Pack*>(src);
+        for (int64_t i = lo / VEC + threadIdx.x; i < hi / VEC; i += blockDim.x) {
+            const Pack pk = v[i];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) s += pk.v[k];
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) s += src[i];
+    }
+    __shared__ T warp_part[8];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T t = threadIdx.x < 8 ? warp_part[threadIdx.x] : T(0);
+        t = warp_sum(t);
+        if (threadIdx.x == 0) {
+            if (segs == 1) d_background[b] = t;
+            else red_add(d_background + b, t);
+        }
+    }
+}
+
+template <typename T>
+static int launch_background_sum(const PullbackArgs<T>& a, int64_t cells, const DeviceInfo& dev) {
+    if (!a.d_background || a.B == 0) return DPR_OK;
+    int64_t segs = 1;
+    const int64_t min_seg = 256 * 16 * 4;  // keep >= 64 KB (f32) of work per CTA
+    if (a.B < (int64_t)dev.sm_count * 4) {
+        segs = ((int64_t)dev.sm_count * 4 + a.B - 1) / a.B;
+        const int64_t max_segs = (cells + min_seg - 1) / min_seg;
+        if (segs > max_segs) segs = max_segs;
+        if (segs < 1) segs = 1;
+    }
+    int64_t seg_len = (cells + segs - 1) / segs;
+    seg_len = (seg_len + 15) / 16 * 16;
+    segs = (cells + seg_len - 1) / seg_len;
+    if (segs < 1) segs = 1;
+    if (segs > 1) DPR_CUDA_TRY(cudaMemsetAsync(a.d_background, 0, sizeof(T) * (size_t)a.B, a.stream));
+    background_sum_kernel<T><<<(unsigned)(a.B * segs), 256, 0, a.stream>>>(a.ds_dout, a.d_background, cells, (int)segs, seg_len);
+    count_launches(1);
+    DPR_CUDA_TRY(cudaGetLastError());
+    return DPR_OK;
+}
+
+template <typename T, int N_IN, int N_OUT>
+static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
+    constexpr int NV = PoseGradLayout<N_IN, N_OUT>::NV;
+    constexpr int K = 4;
+    Grid<T, N_OUT> grid;
+    grid.cells = 1;
+    for (int k = 0; k < N_OUT; ++k) {
+        grid.g[k] = (int)a.grid[k];
+        grid.scale[k] = T(a.grid[k]) / T(2);  // src/raster_pullback.jl:29
+        grid.cells *= a.grid[k];
+    }
+    // zero everything that is accumulated with REDG (ext/DiffPointRasterisationCUDAExt.jl:272-276)
+    DPR_CUDA_TRY(cudaMemsetAsync(a.d_points, 0, sizeof(T) * (size_t)(a.P * N_IN), a.stream));
+    DPR_CUDA_TRY(cudaMemsetAsync(a.d_rotation, 0, sizeof(T) * (size_t)(a.B * N_OUT * N_IN), a.stream));
+    DPR_CUDA_TRY(cudaMemsetAsync(a.d_translation, 0, sizeof(T) * (size_t)(a.B * N_OUT), a.stream));
+    if (a.d_out_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_out_weight, 0, sizeof(T) * (size_t)a.B, a.stream));
+    if (a.d_point_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_point_weight, 0, sizeof(T) * (size_t)a.P, a.stream));
+    int rc = launch_background_sum(a, grid.cells, dev);
+    if (rc != DPR_OK) return rc;
+    if (a.P == 0 || a.B == 0) return DPR_OK;
+
+    const int threads = 256;
+    const int64_t point_chunks = (a.P + (int64_t)threads * K - 1) / ((int64_t)threads * K);
+    // poses per CTA: enough CTAs for ~4 waves of 8 CTAs/SM, but long enough loops to amortise the d_points REDGs
+    int64_t pose_chunk = tuning().pose_chunk;
+    if (pose_chunk <= 0) {
+        const int64_t want_ctas = (int64_t)dev.sm_count * 8 * 4;
+        int64_t pose_chunks = (want_ctas + point_chunks - 1) / point_chunks;
+        if (pose_chunks < 1) pose_chunks = 1;
+        if (pose_chunks > a.B) pose_chunks = a.B;
+        pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
+        if (pose_chunk < 8) pose_chunk = a.B < 8 ? a.B : 8;
+    }
+    if (pose_chunk > 512) pose_chunk = 512;
+    if (pose_chunk > a.B) pose_chunk = a.B;
+    const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
+    if (point_chunks * pose_chunks > (int64_t)0x7fffffff || point_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
+    const size_t smem = sizeof(T) * (size_t)pose_chunk * NV;
+    pullback_gather_global_kernel<T, N_IN, N_OUT, K><<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
+        a.ds_dout, a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.d_points, a.d_rotation,
+        a.d_translation, a.d_out_weight, a.d_point_weight, grid, a.P, a.B, (int)point_chunks, (int)pose_chunk);
+    count_launches(1);
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_PULLBACK, "gather_global");
+    return DPR_OK;
+}
+
+template <typename T>
+int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
+    if (a.n_in == 2 && a.n_out == 2) return pullback_global<T, 2, 2>(a, dev);
+    if (a.n_in == 3 && a.n_out == 2) return pullback_global<T, 3, 2>(a, dev);
+    if (a.n_in == 3 && a.n_out == 3) return pullback_global<T, 3, 3>(a, dev);
+    return DPR_ERR_UNSUPPORTED;
+}
+
+template int pullback_dispatch<float>(const PullbackArgs<float>&, const DeviceInfo&);
+template int pullback_dispatch<double>(const PullbackArgs<double>&, const DeviceInfo&);
+
+size_t pullback_workspace_bytes(int, int, const int64_t*, int64_t, int64_t, int) { return 0; }
+
+}  // namespace dpr

@@ -1,0 +1,132 @@
+/* dpr.h - C ABI of libdpr.so, the B200 (sm_100a) implementation of DiffPointRasterisation.jl's hot path.
+ *
+ * This is the drop-in boundary: the entry points below are what a Julia package extension binds with `ccall`
+ * in place of the kernels of the reference's CUDA extension.  Reference locations are under /root/reference.
+ *
+ * Data layout (identical to the reference's canonical form, i.e. Julia's memory):
+ *   points       Vector{SVector{N_in,T}}          = dense (N_in, P)          column-major
+ *   rotation     Vector{SMatrix{N_out,N_in,T}}    = dense (N_out, N_in, B)   column-major
+ *   translation  Vector{SVector{N_out,T}}         = dense (N_out, B)
+ *   background, out_weight  (B)   - NULL means the FillArrays default Zeros / Ones (src/interface.jl:368-394,
+ *   point_weight            (P)     ext/DiffPointRasterisationCUDAExt.jl:15-17)
+ *   out, ds_dout            (g_1, ..., g_N_out, B) column-major: first grid axis contiguous, pose stride prod(g)
+ *   d_points (N_in, P), d_rotation (N_out, N_in, B), d_translation (N_out, B), d_background (B),
+ *   d_out_weight (B), d_point_weight (P)
+ * All pointers of the device entry points are DEVICE pointers (CuPtr{T} in Julia) valid on the current device.
+ * The caller owns every buffer, including the workspace.  Outputs are fully overwritten (the reference zero-fills
+ * then accumulates: ext/DiffPointRasterisationCUDAExt.jl:272-276; forward overwrites with the background,
+ * src/raster.jl:27), so callers need not pre-zero.  All work is enqueued on `stream`; nothing synchronises.
+ *
+ * Supported: T in {float, double}; (N_in, N_out) in {(2,2), (3,2), (3,3)}.
+ * Return value: DPR_OK (0) or a negative dpr_status; never throws, never aborts.
+ */
+#ifndef DPR_H
+#define DPR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* dpr_stream_t; /* cudaStream_t / CUstream (CUDA.jl: stream().handle) */
+
+enum dpr_status {
+    DPR_OK = 0,
+    DPR_ERR_BAD_DIMS = -1,      /* negative sizes, grid extent < 1, prod(grid)*B overflow            */
+    DPR_ERR_UNSUPPORTED = -2,   /* (N_in, N_out) or element size outside the supported set            */
+    DPR_ERR_NULL_POINTER = -3,  /* a required pointer is NULL                                          */
+    DPR_ERR_WORKSPACE = -4,     /* workspace smaller than dpr_workspace_bytes()                        */
+    DPR_ERR_CUDA = -5,          /* a CUDA runtime call failed; see dpr_last_error_message()            */
+    DPR_ERR_NO_DEVICE = -6,     /* no CUDA device / not an sm_100 device: there is NO CPU fallback     */
+    DPR_ERR_NCCL = -7,          /* a NCCL call failed (multi-GPU entry points only)                    */
+    DPR_ERR_BAD_OPTION = -8
+};
+
+enum dpr_op { DPR_OP_FORWARD = 0, DPR_OP_PULLBACK = 1 };
+
+/* Library/ABI version (major*10000 + minor*100 + patch). */
+int dpr_version(void);
+/* Static string for a status code; for DPR_ERR_CUDA the thread's last CUDA error text is in dpr_last_error_message(). */
+const char* dpr_status_string(int status);
+const char* dpr_last_error_message(void);
+
+/* Scratch the caller must provide (device memory, 256-byte aligned) for one call; may return 0.
+ * Replaces nothing in the reference (CUDA.jl allocates implicitly); the glue allocates a CuVector{UInt8}. */
+size_t dpr_workspace_bytes(int op, int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                           int sizeof_T);
+
+/* Batched forward splat: replaces the canonical `raster!` method src/raster.jl:5-34 and its kernel
+ * src/raster.jl:36-66 (incl. the background broadcast, :27) for CuArray arguments. */
+int dpr_raster_forward_f32(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                           const float* points, const float* rotation, const float* translation,
+                           const float* background, const float* out_weight, const float* point_weight,
+                           float* out, void* workspace, size_t workspace_bytes, dpr_stream_t stream);
+int dpr_raster_forward_f64(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                           const double* points, const double* rotation, const double* translation,
+                           const double* background, const double* out_weight, const double* point_weight,
+                           double* out, void* workspace, size_t workspace_bytes, dpr_stream_t stream);
+
+/* Batched pullback: replaces ext/DiffPointRasterisationCUDAExt.jl:231-321 (driver: sum!, 5 x fill!, launch) and
+ * its kernel :19-210; same gradients as the CPU method src/raster_pullback.jl:85-148.
+ * d_background, d_out_weight and d_point_weight may be NULL (that gradient is then not computed). */
+int dpr_raster_pullback_f32(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                            const float* ds_dout, const float* points, const float* rotation,
+                            const float* translation, const float* out_weight, const float* point_weight,
+                            float* d_points, float* d_rotation, float* d_translation, float* d_background,
+                            float* d_out_weight, float* d_point_weight, void* workspace, size_t workspace_bytes,
+                            dpr_stream_t stream);
+int dpr_raster_pullback_f64(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                            const double* ds_dout, const double* points, const double* rotation,
+                            const double* translation, const double* out_weight, const double* point_weight,
+                            double* d_points, double* d_rotation, double* d_translation, double* d_background,
+                            double* d_out_weight, double* d_point_weight, void* workspace, size_t workspace_bytes,
+                            dpr_stream_t stream);
+
+/* Host-buffer entry points: same semantics, but every pointer is a HOST pointer (the reference's CPU methods
+ * src/raster.jl:5-34 and src/raster_pullback.jl:85-148 take host Arrays).  The library stages pose chunks through
+ * device memory it owns (grown on demand, per device, released by dpr_host_release), overlapping H2D copies,
+ * kernels and D2H copies on internal streams, and returns when the results are in the host buffers.
+ * Pinned buffers (dpr_host_alloc) make the copies asynchronous. */
+int dpr_raster_forward_host_f32(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                const float* points, const float* rotation, const float* translation,
+                                const float* background, const float* out_weight, const float* point_weight,
+                                float* out);
+int dpr_raster_forward_host_f64(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                const double* points, const double* rotation, const double* translation,
+                                const double* background, const double* out_weight, const double* point_weight,
+                                double* out);
+int dpr_raster_pullback_host_f32(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                 const float* ds_dout, const float* points, const float* rotation,
+                                 const float* translation, const float* out_weight, const float* point_weight,
+                                 float* d_points, float* d_rotation, float* d_translation, float* d_background,
+                                 float* d_out_weight, float* d_point_weight);
+int dpr_raster_pullback_host_f64(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                 const double* ds_dout, const double* points, const double* rotation,
+                                 const double* translation, const double* out_weight, const double* point_weight,
+                                 double* d_points, double* d_rotation, double* d_translation, double* d_background,
+                                 double* d_out_weight, double* d_point_weight);
+int dpr_host_alloc(void** ptr, size_t bytes);  /* pinned host memory */
+int dpr_host_free(void* ptr);
+int dpr_host_release(void);                    /* frees the staging arena of the current device */
+
+/* Introspection / tuning (benchmarks and tests). */
+enum dpr_option {
+    DPR_OPT_FORWARD_ALGO = 0,   /* 0 auto, 1 global-reduction kernel, 2 shared-memory tile kernel            */
+    DPR_OPT_PULLBACK_ALGO = 1,  /* 0 auto, 1 gather from global/L2, 2 gather from TMA-staged shared memory    */
+    DPR_OPT_TILE_SMEM_BYTES = 2,/* shared-memory budget per CTA for tiles (0 = default)                       */
+    DPR_OPT_POINT_SPLIT = 3,    /* forward: force the number of point splits per (pose, slab) (0 = auto)      */
+    DPR_OPT_POSE_CHUNK = 4      /* pullback: force poses per CTA (0 = auto)                                   */
+};
+int dpr_set_option(int option, int64_t value);
+int64_t dpr_get_option(int option);
+/* Number of kernels this library has launched in this process (for the bench's gpu_launches claim). */
+int64_t dpr_kernel_launch_count(void);
+/* Name of the kernel path the last forward / pullback call on this thread took (static string). */
+const char* dpr_last_path(int op);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPR_H */

@@ -1,0 +1,86 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library builds, loads, and exports every symbol that
+include/dpr.h declares; host-side argument checking mirrors the reference's errors; no CPU fallback exists."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import dpr_b200
+from dpr_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "dpr.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(dpr_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported():
+    lib = _lib.load()
+    declared = _declared_symbols()
+    assert declared, "no declarations parsed from include/dpr.h"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/dpr.h but not exported by libdpr.so"
+    assert sorted(_lib.SYMBOLS) == declared
+
+
+def test_library_is_sm100a_only():
+    out = os.popen(f"cuobjdump -lelf {_lib.LIB_PATH} 2>/dev/null").read()
+    if out.strip():
+        assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
+
+
+def test_status_strings_and_options():
+    lib = _lib.load()
+    assert lib.dpr_version() >= 100
+    assert lib.dpr_status_string(0) == b"ok"
+    for code in range(-8, 0):
+        assert lib.dpr_status_string(code) not in (b"ok", b"unknown status")
+    assert lib.dpr_set_option(99, 1) == -8 and lib.dpr_set_option(0, 7) == -8
+    _lib.set_option(_lib.OPT_FORWARD_ALGO, 1)
+    assert _lib.get_option(_lib.OPT_FORWARD_ALGO) == 1
+    _lib.set_option(_lib.OPT_FORWARD_ALGO, 0)
+    assert lib.dpr_workspace_bytes(0, 3, 2, (ctypes.c_int64 * 2)(8, 8), 10, 2, 4) == 0
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any CUDA call, so the status codes can be checked on a CPU-only box."""
+    lib = _lib.load()
+    grid = (ctypes.c_int64 * 2)(8, 8)
+    f = lib.dpr_raster_forward_f32
+    assert f(4, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2   # unsupported dims
+    assert f(3, 2, grid, -1, 1, None, None, None, None, None, None, None, None, 0, None) == -1  # bad dims
+    assert f(3, 2, (ctypes.c_int64 * 2)(0, 8), 1, 1, None, None, None, None, None, None, None, None, 0, None) == -1
+    assert f(3, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -3   # NULL pointers
+    assert f(3, 2, None, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -3
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback():
+    pts = torch.zeros(3, 4)
+    rot = torch.zeros(2, 3, 1)
+    tr = torch.zeros(2, 1)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        dpr_b200.raster((8, 8), pts, rot, tr)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        dpr_b200.raster_pullback_(torch.zeros(8, 8, 1), pts, rot, tr)
+    # the C entry point itself reports the missing device instead of computing anything
+    lib = _lib.load()
+    buf = np.zeros(64, dtype=np.float32)
+    p = buf.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.dpr_raster_forward_f32(3, 2, (ctypes.c_int64 * 2)(4, 4), 1, 1, p, p, p, None, None, None, p, None, 0, None)
+    assert rc in (-6, -5)
+
+
+def test_fortran_helpers():
+    t = dpr_b200.empty_f((3, 5, 2), torch.float32, "cpu")
+    assert t.shape == (3, 5, 2) and t.stride() == (1, 3, 15) and dpr_b200.is_fortran(t)
+    c = torch.arange(24.0).reshape(2, 3, 4)
+    f = dpr_b200.fortran(c)
+    assert dpr_b200.is_fortran(f) and torch.equal(f, c)
+    assert np.array_equal(np.asarray(f.permute(2, 1, 0).contiguous()).ravel(), np.asarray(c).ravel(order="F"))

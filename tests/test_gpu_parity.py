@@ -1,0 +1,211 @@
+"""Parity of the CUDA library (through the C ABI) with the CPU oracle and the reference's golden vectors.
+
+Tolerances (BASELINE.json north_star): relative L2 per output array
+  Float64 <= 1e-10 against the faithful Float64 oracle,
+  Float32 <= 1e-5  against the f64-accumulating oracle with the Float32 stencil.
+"""
+import numpy as np
+import pytest
+import torch
+
+import dpr_b200
+from oracle import oracle
+from tests.gpu_util import dev_args, forced, to_dev, to_np
+from tests.helpers import golden_forward_args, make_inputs, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL = {np.float64: 1e-10, np.float32: 1e-5}
+FIELDS = ("points", "rotation", "translation", "background", "out_weight", "point_weight")
+
+
+def _oracle_pair(d, grid, dtype):
+    args = (d["points"], d["rotation"], d["translation"], d["background"], d["out_weight"], d["point_weight"])
+    acc = dtype == np.float32
+    out = oracle.raster(grid, *args, dtype=dtype, n_threads=8, f64_accumulate=acc)
+    pb = oracle.raster_pullback(d["ds_dout"], *args, dtype=dtype, n_slabs=8, f64_accumulate=acc)
+    return out, pb
+
+
+def _check(d, grid, dtype, what=""):
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    out_ref, pb_ref = _oracle_pair(d, grid, dtype)
+    args = dev_args(d, dtype)
+    out = dpr_b200.raster(grid, *args)
+    assert out.dtype == td and tuple(out.shape) == tuple(grid) + (d["rotation"].shape[-1],)
+    e = rel_l2(to_np(out), out_ref)
+    assert e <= TOL[dtype], f"{what} forward [{dpr_b200.last_path(0)}] rel L2 {e:.3e}"
+    pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], td), *args)
+    for k in FIELDS:
+        e = rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k))
+        assert e <= TOL[dtype], f"{what} pullback.{k} [{dpr_b200.last_path(1)}] rel L2 {e:.3e}"
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("algo", [1, 2])
+def test_forward_known_answers(golden, dtype, algo):
+    """The reference's own known-answer tests (src/raster.jl:143-309, README.md:41-68) through the CUDA path."""
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    with forced(forward_algo=algo):
+        for case in golden["forward"]:
+            grid, pts, rot, tr, bg, ow, pw = golden_forward_args(case, dtype)
+            out = dpr_b200.raster(grid, *(to_dev(a, td) for a in (pts, rot, tr, bg, ow, pw)))
+            tol = 1e-12 if dtype == np.float64 else 2e-6
+            np.testing.assert_allclose(to_np(out)[:, :, 0], np.asarray(case["expected"], dtype=np.float64), rtol=0,
+                                       atol=4 * tol, err_msg=case["name"] + " " + case["cite"])
+
+
+def test_pullback_readme_known_answer(golden):
+    g = golden["pullback"]
+    pts = to_dev(np.asarray(g["points"]).T)
+    rot = to_dev(np.asarray(g["rotation"])[:, :, None])
+    tr = to_dev(np.asarray(g["translation"])[:, None])
+    ds = to_dev(np.asarray(g["ds_dout"])[:, :, None])
+    pb = dpr_b200.raster_pullback_(ds, pts, rot, tr)
+    np.testing.assert_allclose(to_np(pb.points), np.asarray(g["d_points"]), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(to_np(pb.rotation)[:, :, 0], np.asarray(g["d_rotation"]), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(to_np(pb.translation)[:, 0], np.asarray(g["d_translation"]), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(to_np(pb.points).T, -np.asarray(g["zygote_d_points"]), rtol=2e-5, atol=2e-5)
+    assert abs(float(pb.background[0]) - np.sum(g["ds_dout"])) < 1e-12
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (64, 48)), (3, 3, (24, 20, 16)), (2, 2, (40, 56))])
+@pytest.mark.parametrize("weights", [True, False])
+def test_parity_random(dtype, n_in, n_out, grid, weights):
+    """Same distributions as the reference's CUDA tests (test/cuda.jl:10-73 with test/data.jl fixtures)."""
+    d = make_inputs(100 + n_in * 10 + n_out, n_in, n_out, 20011, 9, grid, dtype, weights)
+    _check(d, grid, dtype, f"{n_in}->{n_out} {grid}")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("algo,opts", [(1, {}), (2, {}), (2, dict(tile_smem_bytes=48 * 48 * 8)), (2, dict(tile_smem_bytes=13 * 48 * 8)),
+                                       (2, dict(point_split=3)), (2, dict(point_split=3, tile_smem_bytes=40 * 48 * 8))])
+def test_forward_paths_agree(dtype, algo, opts):
+    """Every forward kernel path (global REDG, whole tile, hybrid band, slabs, point splits) gives the oracle's image."""
+    grid = (48, 48)
+    d = make_inputs(42, 3, 2, 30000, 5, grid, dtype)
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    out_ref, _ = _oracle_pair(d, grid, dtype)
+    if dtype == np.float32 and "tile_smem_bytes" in opts:
+        opts = dict(opts, tile_smem_bytes=opts["tile_smem_bytes"] // 2)
+    with forced(forward_algo=algo, **opts):
+        out = dpr_b200.raster(grid, *dev_args(d, dtype))
+        path = dpr_b200.last_path(0)
+    assert rel_l2(to_np(out), out_ref) <= TOL[dtype], path
+    if algo == 1:
+        assert path == "global_redg"
+    else:
+        assert path.startswith("tile2d"), path
+
+
+@pytest.mark.parametrize("pose_chunk", [1, 3, 64])
+def test_pullback_pose_chunking(pose_chunk):
+    grid = (32, 32)
+    d = make_inputs(77, 3, 2, 5000, 11, grid, np.float64)
+    _, pb_ref = _oracle_pair(d, grid, np.float64)
+    with forced(pose_chunk=pose_chunk):
+        pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"]), *dev_args(d, np.float64))
+    for k in FIELDS:
+        assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-10, k
+
+
+def test_batched_equals_singles():
+    """src/raster.jl:383-431, src/raster_pullback.jl:271-345: batch == loop over poses; d_points == sum over poses."""
+    grid = (16, 16, 16)
+    d = make_inputs(5, 3, 3, 4000, 6, grid, np.float64)
+    args = dev_args(d, np.float64)
+    ds = to_dev(d["ds_dout"])
+    out = dpr_b200.raster(grid, *args)
+    pb = dpr_b200.raster_pullback_(ds, *args)
+    acc = torch.zeros_like(pb.points)
+    accw = torch.zeros_like(pb.point_weight)
+    for b in range(6):
+        sl = lambda t: dpr_b200.fortran(t[..., b:b + 1])
+        one = (args[0], sl(args[1]), sl(args[2]), args[3][b:b + 1], args[4][b:b + 1], args[5])
+        out1 = dpr_b200.raster(grid, *one)
+        assert rel_l2(to_np(out1[..., 0]), to_np(out[..., b])) < 1e-13
+        pb1 = dpr_b200.raster_pullback_(sl(ds), *one)
+        assert rel_l2(to_np(pb1.rotation[..., 0]), to_np(pb.rotation[..., b])) < 1e-12
+        assert rel_l2(to_np(pb1.translation[..., 0]), to_np(pb.translation[..., b])) < 1e-12
+        acc += pb1.points
+        accw += pb1.point_weight
+    assert rel_l2(to_np(acc), to_np(pb.points)) < 1e-12 and rel_l2(to_np(accw), to_np(pb.point_weight)) < 1e-12
+
+
+def test_edge_cases():
+    grid = (8, 8)
+    d = make_inputs(9, 3, 2, 37, 3, grid, np.float64)
+    args = dev_args(d, np.float64)
+    # no points: forward is the background, gradients are zero except d_background
+    empty = dpr_b200.empty_f((3, 0), torch.float64, "cuda")
+    out = dpr_b200.raster(grid, empty, args[1], args[2], args[3], args[4], None)
+    assert torch.equal(out, args[3].reshape(1, 1, 3).expand(8, 8, 3))
+    pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"]), empty, args[1], args[2], args[3], args[4], None)
+    assert pb.points.shape == (3, 0) and float(pb.rotation.abs().sum()) == 0
+    np.testing.assert_allclose(to_np(pb.background), d["ds_dout"].sum(axis=(0, 1)), rtol=1e-12)
+    # no poses
+    out0 = dpr_b200.raster(grid, args[0], args[1][..., :0], args[2][..., :0])
+    assert out0.shape == (8, 8, 0)
+    pb0 = dpr_b200.raster_pullback_(dpr_b200.empty_f((8, 8, 0), torch.float64, "cuda"), args[0], args[1][..., :0], args[2][..., :0])
+    assert pb0.points.shape == (3, 37) and float(pb0.points.abs().sum()) == 0
+    # far-away, boundary and non-finite-free points: clipped per corner, no wrap-around (src/raster.jl:62)
+    pts = np.asfortranarray(np.array([[1e30, -1e30, 0.999, -1.0, 1.0, 3.0], [0.0, 0.0, 0.999, -1.0, 1.0, -3.0]]))
+    rot = np.eye(2)[:, :, None]
+    tr = np.zeros((2, 1))
+    for algo in (1, 2):
+        with forced(forward_algo=algo):
+            o = to_np(dpr_b200.raster((4, 4), to_dev(pts), to_dev(rot), to_dev(tr)))
+        np.testing.assert_allclose(o, oracle.raster((4, 4), pts, rot, tr), atol=1e-14)
+    ds = np.random.default_rng(0).standard_normal((4, 4, 1))
+    pbe = dpr_b200.raster_pullback_(to_dev(ds), to_dev(pts), to_dev(rot), to_dev(tr))
+    ref = oracle.raster_pullback(ds, pts, rot, tr)
+    for k in FIELDS:
+        np.testing.assert_allclose(to_np(getattr(pbe, k)), getattr(ref, k), atol=1e-12, err_msg=k)
+
+
+def test_errors_mirror_reference():
+    grid = (8, 8)
+    d = make_inputs(9, 3, 2, 10, 2, grid, np.float64)
+    a = dev_args(d, np.float64)
+    with pytest.raises(dpr_b200.DimensionMismatch):     # src/interface.jl:137-162
+        dpr_b200.raster(grid, a[0], a[1], to_dev(np.zeros((3, 2))))
+    with pytest.raises(dpr_b200.DimensionMismatch):     # src/raster.jl:17-21
+        dpr_b200.raster(grid, a[0], a[1], a[2], a[3][:1])
+    with pytest.raises(dpr_b200.DimensionMismatch):     # src/raster.jl:23
+        dpr_b200.raster(grid, a[0], a[1], a[2], a[3], a[4], a[5][:5])
+    with pytest.raises(dpr_b200.DimensionMismatch):     # src/raster.jl:14
+        dpr_b200.raster((8, 8, 8), a[0], a[1], a[2])
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        dpr_b200.raster(grid, a[0].cpu(), a[1], a[2])
+
+
+def test_preallocated_outputs_and_mixed_precision_promotion():
+    grid = (8, 8)
+    d = make_inputs(9, 3, 2, 100, 2, grid, np.float64)
+    a = dev_args(d, np.float64)
+    ds = to_dev(d["ds_dout"])
+    bufs = dict(points_out=dpr_b200.empty_f((3, 100), torch.float64, "cuda").fill_(7.0),
+                rotation_out=dpr_b200.empty_f((2, 3, 2), torch.float64, "cuda").fill_(7.0))
+    pb = dpr_b200.raster_pullback_(ds, *a, **bufs)
+    assert pb.points.data_ptr() == bufs["points_out"].data_ptr()
+    ref = oracle.raster_pullback(d["ds_dout"], *(d[k] for k in FIELDS))
+    assert rel_l2(to_np(pb.points), ref.points) < 1e-10 and rel_l2(to_np(pb.rotation), ref.rotation) < 1e-10
+    # promotion like src/interface.jl:63-64: Float32 points with Float64 poses compute in Float64
+    out = dpr_b200.raster(grid, a[0].float(), a[1], a[2])
+    assert out.dtype == torch.float64
+
+
+SCALED_CONFIGS = [   # BASELINE.json configs, scaled to sizes the oracle finishes in seconds
+    ("cfg1", 3, 2, 10000, 64, (128, 128), np.float64, False),      # full size: README.md:189
+    ("cfg2", 3, 2, 100000, 8, (256, 256), np.float32, False),      # full P and grid, 8 of 4096 poses
+    ("cfg3", 3, 3, 200000, 2, (64, 64, 64), np.float32, False),
+    ("cfg4", 2, 2, 200000, 4, (512, 512), np.float32, True),
+    ("cfg5", 3, 2, 200000, 32, (128, 128), np.float32, False),
+]
+
+
+@pytest.mark.parametrize("name,n_in,n_out,P,B,grid,dtype,weights", SCALED_CONFIGS)
+def test_baseline_configs_scaled(name, n_in, n_out, P, B, grid, dtype, weights):
+    d = make_inputs(1000 + int(name[-1]), n_in, n_out, P, B, grid, dtype, weights)
+    _check(d, grid, dtype, name)
