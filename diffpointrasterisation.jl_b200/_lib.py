@@ -20,6 +20,7 @@ SYMBOLS = [
     "dpr_raster_forward_host_f32", "dpr_raster_forward_host_f64", "dpr_raster_pullback_host_f32",
     "dpr_raster_pullback_host_f64", "dpr_host_alloc", "dpr_host_free", "dpr_host_release",
     "dpr_set_option", "dpr_get_option", "dpr_kernel_launch_count", "dpr_last_path",
+    "dpr_profile_enable", "dpr_profile_count", "dpr_profile_get",
 ]
 
 OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK = range(5)
@@ -72,6 +73,11 @@ def load() -> ctypes.CDLL:
     lib.dpr_get_option.restype = c_i64
     lib.dpr_get_option.argtypes = [c_i]
     lib.dpr_kernel_launch_count.restype = c_i64
+    lib.dpr_profile_enable.restype = c_i
+    lib.dpr_profile_enable.argtypes = [c_i]
+    lib.dpr_profile_count.restype = c_i
+    lib.dpr_profile_get.restype = c_i
+    lib.dpr_profile_get.argtypes = [c_i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]
     lib.dpr_last_path.restype = ctypes.c_char_p
     lib.dpr_last_path.argtypes = [c_i]
     _lib = lib
@@ -100,3 +106,18 @@ def kernel_launch_count() -> int:
 
 def last_path(op: int) -> str:
     return load().dpr_last_path(op).decode()
+
+
+def profile_enable(on: bool) -> None:
+    check(load().dpr_profile_enable(1 if on else 0))
+
+
+def profile_records():
+    """[(kernel name, milliseconds)] for every launch since profile_enable(True)."""
+    lib = load()
+    out = []
+    for i in range(lib.dpr_profile_count()):
+        name, ms = ctypes.c_char_p(), ctypes.c_float()
+        check(lib.dpr_profile_get(i, ctypes.byref(name), ctypes.byref(ms)))
+        out.append((name.value.decode(), float(ms.value)))
+    return out

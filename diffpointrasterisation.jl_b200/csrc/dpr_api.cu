@@ -19,6 +19,33 @@ const Tuning& tuning() { return g_tuning; }
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 void set_last_path(int op, const char* name) { if (op >= 0 && op < 2) tl_path[op] = name; }
 
+// ---- optional per-kernel event timing -----------------------------------------------------------------
+struct ProfileRecord { const char* name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mutex;
+static std::vector<ProfileRecord> g_prof;
+static std::atomic<int> g_prof_on{0};
+
+LaunchScope::LaunchScope(const char* n, cudaStream_t s) : name(n), stream(s), slot(-1) {
+    count_launches(1);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfileRecord r{n, nullptr, nullptr};
+    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
+    cudaEventRecord(r.e0, s);
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+LaunchScope::~LaunchScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
+}
+static void profile_clear() {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    for (auto& r : g_prof) { if (r.e0) cudaEventDestroy(r.e0); if (r.e1) cudaEventDestroy(r.e1); }
+    g_prof.clear();
+}
+
 int cuda_fail(cudaError_t e, const char* what) {
     snprintf(tl_error, sizeof(tl_error), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     cudaGetLastError();  // clear the sticky-free error state
@@ -311,8 +338,8 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
         int64_t blocks = (n_acc + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
         if (n_acc > 0) {
+            LaunchScope scope("accumulate", s0);
             accumulate_kernel<T><<<(unsigned)blocks, 256, 0, s0>>>(tot_dp, part_dp, n_acc);
-            count_launches(1);
         }
         // the slot's partial buffer may only be reused after the fold: make the slot's stream wait for it
         DPR_CUDA_TRY(cudaEventRecord(done[si], s0));
@@ -462,6 +489,29 @@ int64_t dpr_get_option(int option) {
         case DPR_OPT_POSE_CHUNK: return g_tuning.pose_chunk;
         default: return -1;
     }
+}
+int dpr_profile_enable(int on) {
+    profile_clear();
+    g_prof_on.store(on ? 1 : 0);
+    return DPR_OK;
+}
+int dpr_profile_count(void) {
+    std::lock_guard<std::mutex> lock(g_prof_mutex);
+    return (int)g_prof.size();
+}
+int dpr_profile_get(int i, const char** name, float* ms) {
+    ProfileRecord r;
+    {
+        std::lock_guard<std::mutex> lock(g_prof_mutex);
+        if (i < 0 || i >= (int)g_prof.size()) return DPR_ERR_BAD_OPTION;
+        r = g_prof[i];
+    }
+    DPR_CUDA_TRY(cudaEventSynchronize(r.e1));
+    float t = 0.f;
+    DPR_CUDA_TRY(cudaEventElapsedTime(&t, r.e0, r.e1));
+    if (name) *name = r.name;
+    if (ms) *ms = t;
+    return DPR_OK;
 }
 int64_t dpr_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 const char* dpr_last_path(int op) { return (op >= 0 && op < 2) ? tl_path[op] : "none"; }

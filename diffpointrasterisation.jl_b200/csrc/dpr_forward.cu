@@ -54,9 +54,11 @@ static int launch_fill_background(T* out, const T* background, int64_t cells, in
     int64_t blocks = (n + 255) / 256;
     const int64_t cap = (int64_t)dev.sm_count * 32;
     if (blocks > cap) blocks = cap;
-    if (vec_ok) fill_background_kernel<T, VEC><<<(unsigned)blocks, 256, 0, stream>>>(out, background, cells, n);
-    else fill_background_kernel<T, 1><<<(unsigned)blocks, 256, 0, stream>>>(out, background, cells, n);
-    count_launches(1);
+    {
+        LaunchScope scope("fill_background", stream);
+        if (vec_ok) fill_background_kernel<T, VEC><<<(unsigned)blocks, 256, 0, stream>>>(out, background, cells, n);
+        else fill_background_kernel<T, 1><<<(unsigned)blocks, 256, 0, stream>>>(out, background, cells, n);
+    }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
 }
@@ -239,9 +241,11 @@ static int forward_global(const ForwardArgs<T>& a, const DeviceInfo& dev) {
         pts_per_cta /= 2;
         chunks = (a.P + pts_per_cta - 1) / pts_per_cta;
     }
-    fwd_splat_global_kernel<T, N_IN, N_OUT><<<(unsigned)(chunks * a.B), 256, 0, a.stream>>>(
-        a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.out, grid, a.P, (int)chunks, pts_per_cta);
-    count_launches(1);
+    {
+        LaunchScope scope("fwd_splat_global", a.stream);
+        fwd_splat_global_kernel<T, N_IN, N_OUT><<<(unsigned)(chunks * a.B), 256, 0, a.stream>>>(
+            a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.out, grid, a.P, (int)chunks, pts_per_cta);
+    }
     DPR_CUDA_TRY(cudaGetLastError());
     set_last_path(DPR_OP_FORWARD, "global_redg");
     return DPR_OK;
@@ -300,9 +304,11 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
     auto kern = fwd_splat_tile2d_kernel<T, N_IN>;
     DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     const int64_t ctas = a.B * tp.slabs * tp.splits;
-    kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(a.points, a.rotation, a.translation, a.background,
-                                                         a.out_weight, a.point_weight, a.out, grid, a.P, tp);
-    count_launches(1);
+    {
+        LaunchScope scope("fwd_splat_tile2d", a.stream);
+        kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(a.points, a.rotation, a.translation, a.background,
+                                                             a.out_weight, a.point_weight, a.out, grid, a.P, tp);
+    }
     DPR_CUDA_TRY(cudaGetLastError());
     const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];
     set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid" : (tp.slabs > 1 ? "tile2d_slabs" : (tp.exclusive ? "tile2d" : "tile2d_split")));

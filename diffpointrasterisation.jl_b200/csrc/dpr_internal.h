@@ -26,6 +26,15 @@ struct Tuning {
 const Tuning& tuning();
 int current_device_info(DeviceInfo& info);          // DPR_OK or negative status
 void count_launches(int n);
+// Brackets one kernel launch with CUDA events on its stream when profiling is enabled (dpr_profile_enable), so
+// bench.py can read per-kernel durations live; otherwise only counts the launch.
+struct LaunchScope {
+    LaunchScope(const char* name, cudaStream_t stream);
+    ~LaunchScope();
+    const char* name;
+    cudaStream_t stream;
+    int slot;
+};
 void set_last_path(int op, const char* name);
 int cuda_fail(cudaError_t e, const char* what);     // records the message, returns DPR_ERR_CUDA
 

@@ -205,8 +205,10 @@ static int launch_background_sum(const PullbackArgs<T>& a, int64_t cells, const 
     segs = (cells + seg_len - 1) / seg_len;
     if (segs < 1) segs = 1;
     if (segs > 1) DPR_CUDA_TRY(cudaMemsetAsync(a.d_background, 0, sizeof(T) * (size_t)a.B, a.stream));
-    background_sum_kernel<T><<<(unsigned)(a.B * segs), 256, 0, a.stream>>>(a.ds_dout, a.d_background, cells, (int)segs, seg_len);
-    count_launches(1);
+    {
+        LaunchScope scope("background_sum", a.stream);
+        background_sum_kernel<T><<<(unsigned)(a.B * segs), 256, 0, a.stream>>>(a.ds_dout, a.d_background, cells, (int)segs, seg_len);
+    }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
 }
@@ -249,10 +251,12 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
     if (point_chunks * pose_chunks > (int64_t)0x7fffffff || point_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
     const size_t smem = sizeof(T) * (size_t)pose_chunk * NV;
-    pullback_gather_global_kernel<T, N_IN, N_OUT, K><<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
-        a.ds_dout, a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.d_points, a.d_rotation,
-        a.d_translation, a.d_out_weight, a.d_point_weight, grid, a.P, a.B, (int)point_chunks, (int)pose_chunk);
-    count_launches(1);
+    {
+        LaunchScope scope("pullback_gather_global", a.stream);
+        pullback_gather_global_kernel<T, N_IN, N_OUT, K><<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
+            a.ds_dout, a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.d_points, a.d_rotation,
+            a.d_translation, a.d_out_weight, a.d_point_weight, grid, a.P, a.B, (int)point_chunks, (int)pose_chunk);
+    }
     DPR_CUDA_TRY(cudaGetLastError());
     set_last_path(DPR_OP_PULLBACK, "gather_global");
     return DPR_OK;

@@ -123,6 +123,12 @@ int dpr_set_option(int option, int64_t value);
 int64_t dpr_get_option(int option);
 /* Number of kernels this library has launched in this process (for the bench's gpu_launches claim). */
 int64_t dpr_kernel_launch_count(void);
+/* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed with CUDA events on its stream.
+ * dpr_profile_enable(on) also clears the records; dpr_profile_get synchronises on record i and returns its name
+ * (static string) and duration in milliseconds. */
+int dpr_profile_enable(int on);
+int dpr_profile_count(void);
+int dpr_profile_get(int i, const char** name, float* ms);
 /* Name of the kernel path the last forward / pullback call on this thread took (static string). */
 const char* dpr_last_path(int op);
 
