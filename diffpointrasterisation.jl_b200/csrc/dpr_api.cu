@@ -103,10 +103,10 @@ static int forward_entry(int n_in, int n_out, const int64_t* grid, int64_t P, in
     int rc = check_dims(n_in, n_out, grid, P, B);
     if (rc != DPR_OK) return rc;
     if ((P > 0 && !points) || (B > 0 && (!rotation || !translation || !out))) return DPR_ERR_NULL_POINTER;
-    if (workspace_bytes < forward_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
     DeviceInfo dev;
     rc = current_device_info(dev);
     if (rc != DPR_OK) return rc;
+    if (!workspace || workspace_bytes < forward_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
     ForwardArgs<T> a;
     a.n_in = n_in; a.n_out = n_out;
     for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
@@ -129,10 +129,10 @@ static int pullback_entry(int n_in, int n_out, const int64_t* grid, int64_t P, i
     if (rc != DPR_OK) return rc;
     if ((P > 0 && (!points || !d_points)) || (B > 0 && (!rotation || !translation || !ds_dout || !d_rotation || !d_translation)))
         return DPR_ERR_NULL_POINTER;
-    if (workspace_bytes < pullback_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
     DeviceInfo dev;
     rc = current_device_info(dev);
     if (rc != DPR_OK) return rc;
+    if (workspace_bytes < pullback_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
     PullbackArgs<T> a;
     a.n_in = n_in; a.n_out = n_out;
     for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
@@ -159,6 +159,8 @@ struct HostArena {
     void* shared = nullptr;   size_t shared_bytes = 0;    // points, point_weight, pose-summed gradients
     void* slot[NSTREAM] = {nullptr, nullptr, nullptr};
     size_t slot_bytes = 0;
+    void* ws[NSTREAM] = {nullptr, nullptr, nullptr};   // per-stream kernel workspace (dpr_workspace_bytes)
+    size_t ws_bytes = 0;
 };
 static std::mutex g_arena_mutex;
 static HostArena g_arena[64];
@@ -171,6 +173,8 @@ static int arena_get(HostArena*& out) {
     if (a.device != dev) {
         for (int i = 0; i < NSTREAM; ++i) DPR_CUDA_TRY(cudaStreamCreateWithFlags(&a.streams[i], cudaStreamNonBlocking));
         DPR_CUDA_TRY(cudaEventCreateWithFlags(&a.shared_ready, cudaEventDisableTiming));
+        for (int i = 0; i < NSTREAM; ++i) DPR_CUDA_TRY(cudaMalloc(&a.ws[i], 4096));
+        a.ws_bytes = 4096;
         a.device = dev;
     }
     out = &a;
@@ -245,7 +249,7 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
         if (background) DPR_CUDA_TRY(cudaMemcpyAsync(d_bg, background + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
         if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
         rc = forward_entry<T>(n_in, n_out, grid, P, nb, d_points, d_rot, d_tr, background ? d_bg : nullptr,
-                              out_weight ? d_ow : nullptr, point_weight ? d_pw : nullptr, d_out, nullptr, 0, st);
+                              out_weight ? d_ow : nullptr, point_weight ? d_pw : nullptr, d_out, ar->ws[si], ar->ws_bytes, st);
         if (rc != DPR_OK) break;
         DPR_CUDA_TRY(cudaMemcpyAsync(out + b0 * cells, d_out, sizeof(T) * (size_t)(nb * cells), cudaMemcpyDeviceToHost, st));
     }
@@ -324,7 +328,7 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
         if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
         rc = pullback_entry<T>(n_in, n_out, grid, P, nb, d_img, d_points, d_rot, d_tr, out_weight ? d_ow : nullptr,
                                point_weight ? d_pw : nullptr, part_dp, g_rot, g_tr, h_dbg ? g_bg : nullptr,
-                               h_dow ? g_ow : nullptr, h_dpw ? part_dpw : nullptr, nullptr, 0, st);
+                               h_dow ? g_ow : nullptr, h_dpw ? part_dpw : nullptr, ar->ws[si], ar->ws_bytes, st);
         if (rc != DPR_OK) break;
         DPR_CUDA_TRY(cudaMemcpyAsync(h_drot + b0 * n_out * n_in, g_rot, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyDeviceToHost, st));
         DPR_CUDA_TRY(cudaMemcpyAsync(h_dtr + b0 * n_out, g_tr, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyDeviceToHost, st));
@@ -477,6 +481,7 @@ int dpr_set_option(int option, int64_t value) {
         case DPR_OPT_TILE_SMEM_BYTES: g_tuning.tile_smem_bytes = value; return DPR_OK;
         case DPR_OPT_POINT_SPLIT: g_tuning.point_split = value; return DPR_OK;
         case DPR_OPT_POSE_CHUNK: g_tuning.pose_chunk = value; return DPR_OK;
+        case DPR_OPT_FORWARD_ACCUM: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.forward_accum = value; return DPR_OK;
         default: return DPR_ERR_BAD_OPTION;
     }
 }
@@ -487,6 +492,7 @@ int64_t dpr_get_option(int option) {
         case DPR_OPT_TILE_SMEM_BYTES: return g_tuning.tile_smem_bytes;
         case DPR_OPT_POINT_SPLIT: return g_tuning.point_split;
         case DPR_OPT_POSE_CHUNK: return g_tuning.pose_chunk;
+        case DPR_OPT_FORWARD_ACCUM: return g_tuning.forward_accum;
         default: return -1;
     }
 }

@@ -113,6 +113,16 @@ fwd_splat_global_kernel(const T* __restrict__ points, const T* __restrict__ rota
 // ---------------------------------------------------------------------------------------------------------
 // tile path (2-d): CTA = (pose b, slab s, point split q); slab rows [ys, ye) of the image live in shared memory.
 // Rows outside the band [band_lo, band_hi) (hybrid mode, one slab) are accumulated in L2 with REDG.
+//
+// Two accumulation modes for the shared-memory tile:
+//   float CAS    atomicAdd(float*) on shared memory = LDS + ATOMS.CAST.SPIN loop on sm_100a (no native f32 smem add)
+//   fixed point  (Float32, non-negative weights) contributions are quantised to q = rint(v * 2^F / cmax2) with
+//                cmax2 = the power of two >= out_weight * max(point_weight) and added with the NATIVE 32-bit
+//                ATOMS.ADD (3.4x the CAS rate, profiles/probe_atomics_r01.json).  Integer addition is exact, so the
+//                only error is the quantisation (<= 2^-(F+1) of the largest contribution per splat, F >= 18), and the
+//                result is independent of the order of the atomics.  Wrap-around of a 32-bit cell is detected exactly
+//                by a mass checksum (sum of all quantised contributions == sum of all cells); the CTA then redoes
+//                its slab with the float CAS mode.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct TileParams {
@@ -122,15 +132,105 @@ struct TileParams {
     int band_lo, band_hi;  // rows covered by shared-memory slabs
     int exclusive;    // 1: CTA owns its cells -> flush = store(tile + bg) and it initialises border rows itself
                       // 0: out was pre-filled with the background -> flush = REDG
+    int fixed_bits;   // F > 0: try the fixed-point mode with F fractional bits; 0: float CAS only
+    const float* pw_stats;  // device: {max, min, mean} of point_weight (fixed-point eligibility), or NULL
 };
 
+constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it leaves rint(x) in the low mantissa bits
+constexpr int kMagicBits = 0x4B400000;
+
+template <typename T, int N_IN, bool FIXED>
+__device__ __forceinline__ long long tile_accumulate(T* __restrict__ tile, T* __restrict__ img, const T* __restrict__ points,
+                                                     const T* __restrict__ point_weight, const Pose<T, N_IN, 2>& pose,
+                                                     const Grid<T, 2>& grid, int p_begin, int p_end, int ys, int ye,
+                                                     int band_lo, int band_hi, bool do_border, float qscale) {
+    const int g0 = grid.g[0], g1 = grid.g[1];
+    const int nrows = ye - ys;
+    long long mass = 0;
+    int p = p_begin + threadIdx.x;
+    T xn[N_IN], pwn = T(1);
+    if (p < p_end) {
+        load_point(xn, points, p);
+        if (point_weight) pwn = __ldg(point_weight + p);
+    }
+    while (p < p_end) {
+        T x[N_IN];
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) x[j] = xn[j];
+        const T pw = pwn;
+        const int pn = p + blockDim.x;
+        if (pn < p_end) {   // prefetch the next point while this one is processed
+            load_point(xn, points, pn);
+            if (point_weight) pwn = __ldg(point_weight + pn);
+        }
+        p = pn;
+        int i0[2];
+        T dl[2];
+        if (!stencil(x, pose, grid, i0, dl)) continue;
+        const T weight = pose.ow * pw;                                   // src/raster.jl:51
+        const T du0 = T(1) - dl[0], du1 = T(1) - dl[1];
+        const T v00 = (du0 * du1) * weight, v10 = (dl[0] * du1) * weight;   // src/raster.jl:63, 104-106
+        const T v01 = (du0 * dl[1]) * weight, v11 = (dl[0] * dl[1]) * weight;
+        const int ry = i0[1] - ys;
+        auto tile_add = [&](int off, T v) {
+            if constexpr (FIXED) {
+                const int q = __float_as_int(fmaf((float)v, qscale, kMagic)) - kMagicBits;
+                atomicAdd(reinterpret_cast<int*>(tile) + off, q);
+                mass += q;
+            } else {
+                atomicAdd(tile + off, v);
+            }
+        };
+        if ((unsigned)i0[0] < (unsigned)(g0 - 1) && (unsigned)ry < (unsigned)(nrows - 1)) {
+            // interior of the slab: all four corners are in bounds and on chip
+            const int off = ry * g0 + i0[0];
+            tile_add(off, v00);
+            tile_add(off + 1, v10);
+            tile_add(off + g0, v01);
+            tile_add(off + g0 + 1, v11);
+        } else {
+            const bool x_lo = i0[0] >= 0, x_hi = i0[0] + 1 < g0;
+#pragma unroll
+            for (int cy = 0; cy < 2; ++cy) {
+                const int iy = i0[1] + cy;
+                if (iy < 0 || iy >= g1) continue;                       // per-corner bounds rule, src/raster.jl:62
+                const T va = cy ? v01 : v00, vb = cy ? v11 : v10;
+                if (iy >= ys && iy < ye) {
+                    const int off = (iy - ys) * g0 + i0[0];
+                    if (x_lo) tile_add(off, va);
+                    if (x_hi) tile_add(off + 1, vb);
+                } else if (do_border && (iy < band_lo || iy >= band_hi)) {
+                    T* addr = img + (int64_t)iy * g0 + i0[0];
+                    if (x_lo && x_hi) red_add2(addr, va, vb);
+                    else if (x_lo) red_add(addr, va);
+                    else if (x_hi) red_add(addr + 1, vb);
+                }
+            }
+        }
+    }
+    return mass;
+}
+
+__device__ __forceinline__ long long block_sum_ll(long long v, long long* scratch) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+    __syncthreads();
+    long long t = 0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < nw; ++i) t += scratch[i];
+    return t;
+}
+
 template <typename T, int N_IN>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(1024, 1)
 fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rotation, const T* __restrict__ translation,
                         const T* __restrict__ background, const T* __restrict__ out_weight,
-                        const T* __restrict__ point_weight, T* __restrict__ out, Grid<T, 2> grid, int64_t P,
+                        const T* __restrict__ point_weight, T* __restrict__ out, Grid<T, 2> grid, int P,
                         TileParams<T> tp) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ long long scratch[32];
     T* tile = reinterpret_cast<T*>(smem_raw);
     const int per_pose = tp.slabs * tp.splits;
     const int64_t b = blockIdx.x / per_pose;
@@ -144,7 +244,38 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
     const T bg = background ? __ldg(background + b) : T(0);
     const bool border = (tp.band_lo > 0 || tp.band_hi < g1);
 
-    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile[i] = T(0);
+    Pose<T, N_IN, 2> pose;
+    load_pose(pose, rotation, translation, out_weight, b);
+    const int per_split = (P + tp.splits - 1) / tp.splits;
+    const int p_begin = q * per_split;
+    const int p_end = (p_begin + per_split < P) ? p_begin + per_split : P;
+    const bool do_border = border && s == 0;
+
+    // fixed-point eligibility (uniform across the CTA): Float32, finite positive out_weight, non-negative point
+    // weights of moderate dynamic range
+    bool fixed = false;
+    float qscale = 0.f, inv_qscale = 0.f;
+    if constexpr (sizeof(T) == 4) {
+        if (tp.fixed_bits > 0) {
+            float cmax = (float)pose.ow;
+            bool ok = cmax > 0.f;
+            if (point_weight) {
+                const float wmax = __ldg(tp.pw_stats), wmin = __ldg(tp.pw_stats + 1), wmean = __ldg(tp.pw_stats + 2);
+                ok = ok && wmin >= 0.f && wmax > 0.f && wmax <= 64.f * wmean;
+                cmax *= wmax;
+            }
+            ok = ok && cmax > 1e-30f && cmax < 1e30f;
+            if (ok) {
+                int e;
+                frexpf(cmax, &e);                       // cmax = m * 2^e, m in [0.5, 1)  =>  cmax <= 2^e
+                qscale = ldexpf(1.0f, tp.fixed_bits - e);
+                inv_qscale = ldexpf(1.0f, e - tp.fixed_bits);
+                fixed = true;
+            }
+        }
+    }
+
+    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile[i] = T(0);   // all-zero bits: 0.0f and integer 0
     if (tp.exclusive && border) {
         // this CTA owns the whole pose image (hybrid => one slab, one split): background for the border rows
         const int lo_cells = tp.band_lo * g0;
@@ -154,61 +285,80 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
     }
     __syncthreads();
 
-    Pose<T, N_IN, 2> pose;
-    load_pose(pose, rotation, translation, out_weight, b);
-    const int64_t per_split = (P + tp.splits - 1) / tp.splits;
-    const int64_t p_begin = (int64_t)q * per_split;
-    const int64_t p_end = (p_begin + per_split < P) ? p_begin + per_split : P;
-    const bool do_border = border && s == 0;
-    for (int64_t p = p_begin + threadIdx.x; p < p_end; p += blockDim.x) {
-        T x[N_IN];
-        load_point(x, points, p);
-        int i0[2];
-        T dl[2], du[2];
-        if (!stencil(x, pose, grid, i0, dl)) continue;
-        const T weight = pose.ow * (point_weight ? __ldg(point_weight + p) : T(1));
-        du[0] = T(1) - dl[0];
-        du[1] = T(1) - dl[1];
-        const bool x_lo = i0[0] >= 0, x_hi = i0[0] + 1 < g0;
-#pragma unroll
-        for (int cy = 0; cy < 2; ++cy) {
-            const int iy = i0[1] + cy;
-            if (iy < 0 || iy >= g1) continue;
-            const T v0 = corner_weight<T, 2>(cy << 1, dl, du) * weight;
-            const T v1 = corner_weight<T, 2>((cy << 1) | 1, dl, du) * weight;
-            if (iy >= ys && iy < ye) {
-                T* addr = tile + (iy - ys) * g0 + i0[0];
-                if (x_lo) atomicAdd(addr, v0);
-                if (x_hi) atomicAdd(addr + 1, v1);
-            } else if (do_border && (iy < tp.band_lo || iy >= tp.band_hi)) {
-                T* addr = img + (int64_t)iy * g0 + i0[0];
-                if (x_lo && x_hi) red_add2(addr, v0, v1);
-                else if (x_lo) red_add(addr, v0);
-                else if (x_hi) red_add(addr + 1, v1);
-            }
+    if (fixed) {
+        long long mass = tile_accumulate<T, N_IN, true>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
+                                                        tp.band_lo, tp.band_hi, do_border, qscale);
+        mass = block_sum_ll(mass, scratch);       // contains the __syncthreads that ends the accumulation phase
+        long long cells_sum = 0;
+        for (int i = threadIdx.x; i < n_tile; i += blockDim.x) cells_sum += reinterpret_cast<const int*>(tile)[i];
+        cells_sum = block_sum_ll(cells_sum, scratch);
+        if (cells_sum != mass) {
+            // a 32-bit cell wrapped: redo this slab in float (border splats were already sent, do not resend)
+            fixed = false;
+            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile[i] = T(0);
+            __syncthreads();
+            tile_accumulate<T, N_IN, false>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
+                                            tp.band_lo, tp.band_hi, false, 0.f);
+            __syncthreads();
         }
+    } else {
+        tile_accumulate<T, N_IN, false>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
+                                        tp.band_hi, do_border, 0.f);
+        __syncthreads();
     }
-    __syncthreads();
 
+    auto cell_value = [&](int i) -> T {
+        if constexpr (sizeof(T) == 4) {
+            if (fixed) return (T)((float)reinterpret_cast<const int*>(tile)[i] * inv_qscale);
+        }
+        return tile[i];
+    };
     T* __restrict__ dst = img + (int64_t)ys * g0;
     if (tp.exclusive) {
         constexpr int VEC = 16 / sizeof(T);
         struct alignas(16) Pack { T v[VEC]; };
         if ((n_tile % VEC) == 0 && (reinterpret_cast<uintptr_t>(dst) % 16) == 0) {
             for (int i = threadIdx.x; i < n_tile / VEC; i += blockDim.x) {
-                Pack pk = reinterpret_cast<const Pack*>(tile)[i];
+                Pack pk;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) pk.v[k] += bg;
+                for (int k = 0; k < VEC; ++k) pk.v[k] = cell_value(i * VEC + k) + bg;
                 reinterpret_cast<Pack*>(dst)[i] = pk;
             }
         } else {
-            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) dst[i] = tile[i] + bg;
+            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) dst[i] = cell_value(i) + bg;
         }
     } else {
         for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
-            const T v = tile[i];
+            const T v = cell_value(i);
             if (v != T(0)) red_add(dst + i, v);
         }
+    }
+}
+
+// {max, min, mean} of point_weight, for the fixed-point eligibility test (single CTA; P floats are a few MB at most)
+__global__ void __launch_bounds__(1024) point_weight_stats_kernel(const float* __restrict__ pw, int64_t P, float* __restrict__ stats) {
+    float mx = -3.4e38f, mn = 3.4e38f;
+    double sum = 0.0;
+    for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+        const float w = __ldg(pw + i);
+        mx = fmaxf(mx, w);
+        mn = fminf(mn, w);
+        sum += (double)w;
+        if (!(w == w)) mn = -1.f;    // NaN weights disable the fixed-point mode
+    }
+    __shared__ float smx[32], smn[32];
+    __shared__ double ssum[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; smn[threadIdx.x >> 5] = mn; ssum[threadIdx.x >> 5] = sum; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 1; i < 32; ++i) { mx = fmaxf(mx, smx[i]); mn = fminf(mn, smn[i]); sum += ssum[i]; }
+        stats[0] = mx; stats[1] = mn; stats[2] = (float)(sum / (double)(P > 0 ? P : 1));
     }
 }
 
@@ -259,7 +409,7 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
     if (budget > (int64_t)dev.max_smem_optin) budget = dev.max_smem_optin;
     const int64_t row_bytes = g0 * (int64_t)sizeof(T);
     const int64_t rows_fit = budget / row_bytes;
-    if (rows_fit < 8 || g0 * g1 > (int64_t)0x3fffffff) return false;
+    if (rows_fit < 8 || g0 * g1 > (int64_t)0x3fffffff || a.P > (int64_t)0x3fffffff) return false;
     tp.band_lo = 0;
     tp.band_hi = (int)g1;
     if (rows_fit >= g1) {
@@ -290,6 +440,15 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
     if (a.B * tp.slabs * Q > (int64_t)0x7fffffff) return false;
     tp.splits = (int)Q;
     tp.exclusive = (Q == 1) ? 1 : 0;
+    // fixed-point fractional bits: headroom for ~64x the mean number of points per cell before a 32-bit cell wraps
+    tp.fixed_bits = 0;
+    tp.pw_stats = nullptr;
+    if (sizeof(T) == 4 && tuning().forward_accum != 1) {
+        const double per_cell = (double)a.P / (double)(g0 * g1);
+        int head = 6;
+        while (head < 13 && (double)(1 << head) < 64.0 * per_cell + 64.0) ++head;
+        tp.fixed_bits = 31 - head > 22 ? 22 : 31 - head;
+    }
     smem_bytes = (size_t)tp.rows * (size_t)row_bytes;
     return true;
 }
@@ -301,17 +460,33 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
         int rc = launch_fill_background(a.out, a.background, grid.cells, a.B, dev, a.stream);
         if (rc != DPR_OK) return rc;
     }
+    TileParams<T> tpl = tp;
+    if (tpl.fixed_bits > 0 && a.point_weight) {
+        if (a.workspace && a.workspace_bytes >= 16) {
+            if constexpr (sizeof(T) == 4) {
+                LaunchScope scope("point_weight_stats", a.stream);
+                point_weight_stats_kernel<<<1, 1024, 0, a.stream>>>(reinterpret_cast<const float*>(a.point_weight), a.P,
+                                                                    static_cast<float*>(a.workspace));
+            }
+            tpl.pw_stats = static_cast<const float*>(a.workspace);
+        } else {
+            tpl.fixed_bits = 0;   // no scratch for the statistics: float accumulation
+        }
+    }
     auto kern = fwd_splat_tile2d_kernel<T, N_IN>;
     DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     const int64_t ctas = a.B * tp.slabs * tp.splits;
     {
         LaunchScope scope("fwd_splat_tile2d", a.stream);
         kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(a.points, a.rotation, a.translation, a.background,
-                                                             a.out_weight, a.point_weight, a.out, grid, a.P, tp);
+                                                             a.out_weight, a.point_weight, a.out, grid, (int)a.P, tpl);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];
-    set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid" : (tp.slabs > 1 ? "tile2d_slabs" : (tp.exclusive ? "tile2d" : "tile2d_split")));
+    if (tpl.fixed_bits > 0)
+        set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid_fixed" : (tp.slabs > 1 ? "tile2d_slabs_fixed" : (tp.exclusive ? "tile2d_fixed" : "tile2d_split_fixed")));
+    else
+        set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid" : (tp.slabs > 1 ? "tile2d_slabs" : (tp.exclusive ? "tile2d" : "tile2d_split")));
     return DPR_OK;
 }
 
@@ -335,6 +510,6 @@ int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
 template int forward_dispatch<float>(const ForwardArgs<float>&, const DeviceInfo&);
 template int forward_dispatch<double>(const ForwardArgs<double>&, const DeviceInfo&);
 
-size_t forward_workspace_bytes(int, int, const int64_t*, int64_t, int64_t, int) { return 0; }
+size_t forward_workspace_bytes(int, int, const int64_t*, int64_t, int64_t, int) { return 256; }
 
 }  // namespace dpr

@@ -106,6 +106,24 @@ def _grid_array(grid_size):
     return (ctypes.c_int64 * len(grid_size))(*[int(g) for g in grid_size])
 
 
+_workspaces = {}
+
+
+def _workspace(op: int, n_in, n_out, grid, P, B, dtype, device):
+    """Scratch buffer of dpr_workspace_bytes() for one call (cached per device and stream; the glue owns it, like the
+    CuVector{UInt8} a Julia caller would allocate)."""
+    lib = _lib.load()
+    need = int(lib.dpr_workspace_bytes(op, n_in, n_out, grid, P, B, 4 if dtype == torch.float32 else 8))
+    if need == 0:
+        return None, 0
+    key = (device, torch.cuda.current_stream(device).cuda_stream, op)
+    buf = _workspaces.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(max(need, 4096), dtype=torch.uint8, device=device)
+        _workspaces[key] = buf
+    return buf, buf.numel()
+
+
 def _stream_handle(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
@@ -130,8 +148,11 @@ def raster_(out: torch.Tensor, points, rotation, translation, background=None, o
     lib = _lib.load()
     with torch.cuda.device(device):
         fn = getattr(lib, f"dpr_raster_forward_{suf}")
-        rc = fn(n_in, n_out, _grid_array(out.shape[:-1]), P, B, _ptr(points), _ptr(rotation), _ptr(translation),
-                _ptr(background), _ptr(out_weight), _ptr(point_weight), _ptr(out), None, 0, _stream_handle(device))
+        garr = _grid_array(out.shape[:-1])
+        ws, ws_bytes = _workspace(_lib.OP_FORWARD, n_in, n_out, garr, P, B, dtype, device)
+        rc = fn(n_in, n_out, garr, P, B, _ptr(points), _ptr(rotation), _ptr(translation),
+                _ptr(background), _ptr(out_weight), _ptr(point_weight), _ptr(out), _ptr(ws), ws_bytes,
+                _stream_handle(device))
     _lib.check(rc)
     return out
 
@@ -199,9 +220,11 @@ def raster_pullback_(ds_dout: torch.Tensor, points, rotation, translation, backg
     lib = _lib.load()
     with torch.cuda.device(device):
         fn = getattr(lib, f"dpr_raster_pullback_{suf}")
-        rc = fn(n_in, n_out, _grid_array(ds_dout.shape[:-1]), P, B, _ptr(ds_dout), _ptr(points), _ptr(rotation),
+        garr = _grid_array(ds_dout.shape[:-1])
+        ws, ws_bytes = _workspace(_lib.OP_PULLBACK, n_in, n_out, garr, P, B, dtype, device)
+        rc = fn(n_in, n_out, garr, P, B, _ptr(ds_dout), _ptr(points), _ptr(rotation),
                 _ptr(translation), _ptr(out_weight), _ptr(point_weight), _ptr(res.points), _ptr(res.rotation),
-                _ptr(res.translation), _ptr(res.background), _ptr(res.out_weight), _ptr(res.point_weight), None, 0,
-                _stream_handle(device))
+                _ptr(res.translation), _ptr(res.background), _ptr(res.out_weight), _ptr(res.point_weight), _ptr(ws),
+                ws_bytes, _stream_handle(device))
     _lib.check(rc)
     return res

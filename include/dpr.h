@@ -117,7 +117,8 @@ enum dpr_option {
     DPR_OPT_PULLBACK_ALGO = 1,  /* 0 auto, 1 gather from global/L2, 2 gather from TMA-staged shared memory    */
     DPR_OPT_TILE_SMEM_BYTES = 2,/* shared-memory budget per CTA for tiles (0 = default)                       */
     DPR_OPT_POINT_SPLIT = 3,    /* forward: force the number of point splits per (pose, slab) (0 = auto)      */
-    DPR_OPT_POSE_CHUNK = 4      /* pullback: force poses per CTA (0 = auto)                                   */
+    DPR_OPT_POSE_CHUNK = 4,     /* pullback: force poses per CTA (0 = auto)                                   */
+    DPR_OPT_FORWARD_ACCUM = 5   /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
 };
 int dpr_set_option(int option, int64_t value);
 int64_t dpr_get_option(int option);

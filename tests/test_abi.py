@@ -45,7 +45,7 @@ def test_status_strings_and_options():
     _lib.set_option(_lib.OPT_FORWARD_ALGO, 1)
     assert _lib.get_option(_lib.OPT_FORWARD_ALGO) == 1
     _lib.set_option(_lib.OPT_FORWARD_ALGO, 0)
-    assert lib.dpr_workspace_bytes(0, 3, 2, (ctypes.c_int64 * 2)(8, 8), 10, 2, 4) == 0
+    assert lib.dpr_workspace_bytes(0, 3, 2, (ctypes.c_int64 * 2)(8, 8), 10, 2, 4) <= 4096
 
 
 def test_argument_validation_without_gpu():

@@ -99,6 +99,55 @@ def test_forward_paths_agree(dtype, algo, opts):
         assert path.startswith("tile2d"), path
 
 
+@pytest.mark.parametrize("weights", [True, False])
+def test_forward_fixed_point_and_float_accumulation_agree(weights):
+    """Float32 tile kernel: the native-integer (fixed-point) accumulation and the float CAS accumulation both meet
+    the Float32 gate, and the fixed-point result is bit-reproducible from run to run."""
+    grid = (96, 80)
+    d = make_inputs(314, 3, 2, 60000, 7, grid, np.float32, weights)
+    out_ref, _ = _oracle_pair(d, grid, np.float32)
+    args = dev_args(d, np.float32)
+    with forced(forward_algo=2, forward_accum=0):
+        a1 = dpr_b200.raster(grid, *args)
+        path_fixed = dpr_b200.last_path(0)
+        a2 = dpr_b200.raster(grid, *args)
+    with forced(forward_algo=2, forward_accum=1):
+        b = dpr_b200.raster(grid, *args)
+        path_float = dpr_b200.last_path(0)
+    assert path_fixed.endswith("_fixed") and not path_float.endswith("_fixed")
+    assert rel_l2(to_np(a1), out_ref) <= 1e-5 and rel_l2(to_np(b), out_ref) <= 1e-5
+    assert torch.equal(a1, a2), "integer accumulation must not depend on the order of the atomics"
+
+
+@pytest.mark.parametrize("case", ["wrap", "negative_out_weight", "negative_point_weight", "wide_dynamic_range", "zero_weight"])
+def test_forward_fixed_point_fallbacks(case):
+    """Inputs the fixed-point mode must not mishandle: a cell that wraps 32 bits (thousands of coincident points),
+    negative or wildly varying weights (mode not eligible), zero out_weight."""
+    grid = (32, 32)
+    rng = np.random.default_rng(1)
+    P, B = 30000, 3
+    pts = np.asfortranarray((0.3 * rng.standard_normal((3, P))).astype(np.float32))
+    d = make_inputs(2, 3, 2, P, B, grid, np.float32)
+    ow, pw = d["out_weight"].copy(), None
+    if case == "wrap":
+        pts[:, :20000] = np.array([[0.013], [0.021], [0.0]], dtype=np.float32)   # 20000 points in one pixel
+    elif case == "negative_out_weight":
+        ow[1] = -ow[1]
+    elif case == "negative_point_weight":
+        pw = rng.standard_normal(P).astype(np.float32)
+    elif case == "wide_dynamic_range":
+        pw = np.exp(8 * rng.standard_normal(P)).astype(np.float32)
+    elif case == "zero_weight":
+        ow[0] = 0.0
+    ref = oracle.raster(grid, pts, d["rotation"], d["translation"], d["background"], ow, pw, dtype=np.float32, f64_accumulate=True)
+    with forced(forward_algo=2, forward_accum=0):
+        out = dpr_b200.raster(grid, *(to_dev(a) for a in (pts, d["rotation"], d["translation"], d["background"], ow, pw)))
+    assert rel_l2(to_np(out), ref) <= 1e-5, case
+    # the per-pixel relative accuracy must survive too where pixels are well above the noise floor
+    big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    assert np.max(np.abs(to_np(out)[big] - ref[big]) / np.abs(ref[big])) < 2e-4, case
+
+
 @pytest.mark.parametrize("pose_chunk", [1, 3, 64])
 def test_pullback_pose_chunking(pose_chunk):
     grid = (32, 32)
