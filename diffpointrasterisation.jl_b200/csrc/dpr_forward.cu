@@ -229,8 +229,7 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
                         const T* __restrict__ background, const T* __restrict__ out_weight,
                         const T* __restrict__ point_weight, T* __restrict__ out, Grid<T, 2> grid, int P,
                         TileParams<T> tp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ long long scratch[32];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
     const int per_pose = tp.slabs * tp.splits;
     const int64_t b = blockIdx.x / per_pose;
@@ -251,30 +250,6 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
     const int p_end = (p_begin + per_split < P) ? p_begin + per_split : P;
     const bool do_border = border && s == 0;
 
-    // fixed-point eligibility (uniform across the CTA): Float32, finite positive out_weight, non-negative point
-    // weights of moderate dynamic range
-    bool fixed = false;
-    float qscale = 0.f, inv_qscale = 0.f;
-    if constexpr (sizeof(T) == 4) {
-        if (tp.fixed_bits > 0) {
-            float cmax = (float)pose.ow;
-            bool ok = cmax > 0.f;
-            if (point_weight) {
-                const float wmax = __ldg(tp.pw_stats), wmin = __ldg(tp.pw_stats + 1), wmean = __ldg(tp.pw_stats + 2);
-                ok = ok && wmin >= 0.f && wmax > 0.f && wmax <= 64.f * wmean;
-                cmax *= wmax;
-            }
-            ok = ok && cmax > 1e-30f && cmax < 1e30f;
-            if (ok) {
-                int e;
-                frexpf(cmax, &e);                       // cmax = m * 2^e, m in [0.5, 1)  =>  cmax <= 2^e
-                qscale = ldexpf(1.0f, tp.fixed_bits - e);
-                inv_qscale = ldexpf(1.0f, e - tp.fixed_bits);
-                fixed = true;
-            }
-        }
-    }
-
     for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile[i] = T(0);   // all-zero bits: 0.0f and integer 0
     if (tp.exclusive && border) {
         // this CTA owns the whole pose image (hybrid => one slab, one split): background for the border rows
@@ -285,34 +260,11 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
     }
     __syncthreads();
 
-    if (fixed) {
-        long long mass = tile_accumulate<T, N_IN, true>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
-                                                        tp.band_lo, tp.band_hi, do_border, qscale);
-        mass = block_sum_ll(mass, scratch);       // contains the __syncthreads that ends the accumulation phase
-        long long cells_sum = 0;
-        for (int i = threadIdx.x; i < n_tile; i += blockDim.x) cells_sum += reinterpret_cast<const int*>(tile)[i];
-        cells_sum = block_sum_ll(cells_sum, scratch);
-        if (cells_sum != mass) {
-            // a 32-bit cell wrapped: redo this slab in float (border splats were already sent, do not resend)
-            fixed = false;
-            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile[i] = T(0);
-            __syncthreads();
-            tile_accumulate<T, N_IN, false>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
-                                            tp.band_lo, tp.band_hi, false, 0.f);
-            __syncthreads();
-        }
-    } else {
-        tile_accumulate<T, N_IN, false>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
-                                        tp.band_hi, do_border, 0.f);
-        __syncthreads();
-    }
+    tile_accumulate<T, N_IN, false>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
+                                    tp.band_hi, do_border, 0.f);
+    __syncthreads();
 
-    auto cell_value = [&](int i) -> T {
-        if constexpr (sizeof(T) == 4) {
-            if (fixed) return (T)((float)reinterpret_cast<const int*>(tile)[i] * inv_qscale);
-        }
-        return tile[i];
-    };
+    auto cell_value = [&](int i) -> T { return tile[i]; };
     T* __restrict__ dst = img + (int64_t)ys * g0;
     if (tp.exclusive) {
         constexpr int VEC = 16 / sizeof(T);
@@ -362,6 +314,10 @@ __global__ void __launch_bounds__(1024) point_weight_stats_kernel(const float* _
     }
 }
 
+}  // namespace dpr
+#include "dpr_forward_fast.cuh"
+namespace dpr {
+
 // ---------------------------------------------------------------------------------------------------------
 // host-side planning + dispatch
 // ---------------------------------------------------------------------------------------------------------
@@ -403,10 +359,15 @@ static int forward_global(const ForwardArgs<T>& a, const DeviceInfo& dev) {
 
 // Decide whether (and how) the 2-d tile kernel applies. Returns false if the global path should be used.
 template <typename T>
-static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TileParams<T>& tp, size_t& smem_bytes) {
+static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TileParams<T>& tp, size_t& smem_bytes, bool& use_fast) {
     const int64_t g0 = a.grid[0], g1 = a.grid[1];
     int64_t budget = tuning().tile_smem_bytes > 0 ? tuning().tile_smem_bytes : (int64_t)dev.max_smem_optin - 1024;
-    if (budget > (int64_t)dev.max_smem_optin) budget = dev.max_smem_optin;
+    if (budget > (int64_t)dev.max_smem_optin - 1024) budget = (int64_t)dev.max_smem_optin - 1024;
+    // Float32 with 16-byte aligned inputs takes the TMA-staged fixed-point kernel, which needs staging space
+    use_fast = sizeof(T) == 4 && tuning().forward_accum != 1 && (reinterpret_cast<uintptr_t>(a.points) & 15) == 0 &&
+               (!a.point_weight || ((reinterpret_cast<uintptr_t>(a.point_weight) & 15) == 0 && a.workspace && a.workspace_bytes >= 16));
+    const int64_t extra = use_fast ? (int64_t)fast_extra_smem(a.n_in, a.point_weight != nullptr) + 128 : 0;
+    if (use_fast && tuning().tile_smem_bytes == 0) budget -= extra;
     const int64_t row_bytes = g0 * (int64_t)sizeof(T);
     const int64_t rows_fit = budget / row_bytes;
     if (rows_fit < 8 || g0 * g1 > (int64_t)0x3fffffff || a.P > (int64_t)0x3fffffff) return false;
@@ -443,13 +404,14 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
     // fixed-point fractional bits: headroom for ~64x the mean number of points per cell before a 32-bit cell wraps
     tp.fixed_bits = 0;
     tp.pw_stats = nullptr;
-    if (sizeof(T) == 4 && tuning().forward_accum != 1) {
+    if (use_fast) {
         const double per_cell = (double)a.P / (double)(g0 * g1);
         int head = 6;
-        while (head < 13 && (double)(1 << head) < 64.0 * per_cell + 64.0) ++head;
-        tp.fixed_bits = 31 - head > 22 ? 22 : 31 - head;
+        while (head < 14 && (double)(1 << head) < 64.0 * per_cell + 64.0) ++head;
+        tp.fixed_bits = 32 - head > 22 ? 22 : 32 - head;     // cells are unsigned 32-bit
     }
     smem_bytes = (size_t)tp.rows * (size_t)row_bytes;
+    if (use_fast) smem_bytes = (smem_bytes + 127) / 128 * 128 + (size_t)extra;
     return true;
 }
 
@@ -461,18 +423,7 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
         if (rc != DPR_OK) return rc;
     }
     TileParams<T> tpl = tp;
-    if (tpl.fixed_bits > 0 && a.point_weight) {
-        if (a.workspace && a.workspace_bytes >= 16) {
-            if constexpr (sizeof(T) == 4) {
-                LaunchScope scope("point_weight_stats", a.stream);
-                point_weight_stats_kernel<<<1, 1024, 0, a.stream>>>(reinterpret_cast<const float*>(a.point_weight), a.P,
-                                                                    static_cast<float*>(a.workspace));
-            }
-            tpl.pw_stats = static_cast<const float*>(a.workspace);
-        } else {
-            tpl.fixed_bits = 0;   // no scratch for the statistics: float accumulation
-        }
-    }
+    tpl.fixed_bits = 0;
     auto kern = fwd_splat_tile2d_kernel<T, N_IN>;
     DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     const int64_t ctas = a.B * tp.slabs * tp.splits;
@@ -483,10 +434,42 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
     }
     DPR_CUDA_TRY(cudaGetLastError());
     const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];
-    if (tpl.fixed_bits > 0)
-        set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid_fixed" : (tp.slabs > 1 ? "tile2d_slabs_fixed" : (tp.exclusive ? "tile2d_fixed" : "tile2d_split_fixed")));
-    else
-        set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid" : (tp.slabs > 1 ? "tile2d_slabs" : (tp.exclusive ? "tile2d" : "tile2d_split")));
+    set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid" : (tp.slabs > 1 ? "tile2d_slabs" : (tp.exclusive ? "tile2d" : "tile2d_split")));
+    return DPR_OK;
+}
+
+// Float32 fast path: TMA-staged points, packed FP32x2 stencil, fixed-point native shared-memory atomics
+template <int N_IN>
+static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& dev, const TileParams<float>& tp, size_t smem_bytes) {
+    const Grid<float, 2> grid = make_grid<float, 2>(a.grid);
+    if (!tp.exclusive) {
+        int rc = launch_fill_background(a.out, a.background, grid.cells, a.B, dev, a.stream);
+        if (rc != DPR_OK) return rc;
+    }
+    FastTileParams fp;
+    fp.slabs = tp.slabs; fp.splits = tp.splits; fp.rows = tp.rows; fp.band_lo = tp.band_lo; fp.band_hi = tp.band_hi;
+    fp.exclusive = tp.exclusive; fp.fixed_bits = tp.fixed_bits; fp.pw_stats = nullptr;
+    const int64_t per_split = ((a.P + tp.splits - 1) / tp.splits + kChunk - 1) / kChunk * kChunk;
+    fp.per_split = (int)per_split;
+    const bool has_pw = a.point_weight != nullptr;
+    if (has_pw) {
+        LaunchScope scope("point_weight_stats", a.stream);
+        point_weight_stats_kernel<<<1, 1024, 0, a.stream>>>(a.point_weight, a.P, static_cast<float*>(a.workspace));
+        fp.pw_stats = static_cast<const float*>(a.workspace);
+    }
+    const int64_t ctas = a.B * tp.slabs * tp.splits;
+    auto launch = [&](auto kern) -> int {
+        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        LaunchScope scope("fwd_tile2d_fast", a.stream);
+        kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(a.points, a.rotation, a.translation, a.background,
+                                                             a.out_weight, a.point_weight, a.out, grid, (int)a.P, fp);
+        return DPR_OK;
+    };
+    int rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true>) : launch(fwd_tile2d_fast_kernel<N_IN, false>);
+    if (rc != DPR_OK) return rc;
+    DPR_CUDA_TRY(cudaGetLastError());
+    const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];
+    set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid_fixed" : (tp.slabs > 1 ? "tile2d_slabs_fixed" : (tp.exclusive ? "tile2d_fixed" : "tile2d_split_fixed")));
     return DPR_OK;
 }
 
@@ -496,7 +479,12 @@ int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
     if (a.n_out == 2 && algo != 1 && a.P > 0 && a.B > 0) {
         TileParams<T> tp;
         size_t smem = 0;
-        if (plan_tile2d(a, dev, tp, smem)) {
+        bool use_fast = false;
+        if (plan_tile2d(a, dev, tp, smem, use_fast)) {
+            if constexpr (sizeof(T) == 4) {
+                if (use_fast && a.n_in == 2) return forward_tile2d_fast<2>(a, dev, tp, smem);
+                if (use_fast && a.n_in == 3) return forward_tile2d_fast<3>(a, dev, tp, smem);
+            }
             if (a.n_in == 2) return forward_tile2d<T, 2>(a, dev, tp, smem);
             if (a.n_in == 3) return forward_tile2d<T, 3>(a, dev, tp, smem);
         }

@@ -1,0 +1,305 @@
+// dpr_forward_fast.cuh - the Float32 2-d forward splat kernel tuned for sm_100a (included by dpr_forward.cu).
+//
+// Same decomposition as fwd_splat_tile2d_kernel (CTA = pose x slab x point split, slab accumulated in shared
+// memory, one coalesced flush), with the inner loop rebuilt around what the ncu captures of that kernel showed
+// (profiles/): it was bound by issue slots, not by memory.
+//   * points arrive through TMA: one elected thread issues cp.async.bulk (UBLKCP) per 1024-point chunk into a
+//     shared-memory stage guarded by a full/empty mbarrier pair; every thread then reads its point with three
+//     conflict-free LDS instead of three strided LDG (which cost 3x the L2 sectors with no L1 left beside the tile);
+//   * the transform and the stencil run on Blackwell's packed FP32x2 pipe (FMUL2/FADD2/FFMA2: both output
+//     dimensions in one instruction), still unfused and in the reference's operation order, so cell assignment is
+//     bit-identical to the scalar path (dpr_common.cuh::stencil);
+//   * accumulation is fixed-point on the native 32-bit ATOMS.ADD (see dpr_forward.cu header comment); a 64-bit mass
+//     checksum detects a wrapped cell exactly and the CTA then redoes the slab with float CAS atomics;
+//   * the ~5% of lanes whose stencil leaves the slab (image border, slab edge) are not handled inline - that made
+//     almost every warp execute the slow path - but compacted into a per-warp queue and processed 32 at a time.
+#pragma once
+#include "dpr_common.cuh"
+
+namespace dpr {
+
+constexpr int kChunk = 1024;          // points per TMA chunk = threads per CTA
+constexpr int kQueueCap = 64;         // per-warp deferred-point queue (ints)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-d bulk copy global -> shared through the TMA unit, completion counted in bytes on `bar`
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+struct FastTileParams {
+    int slabs, splits, rows, band_lo, band_hi, exclusive;
+    int fixed_bits;
+    int per_split;             // points per split, a multiple of kChunk
+    const float* pw_stats;     // {max, min, mean} of point_weight or NULL
+};
+
+// shared-memory carve-up (bytes) after the tile
+__host__ __device__ inline size_t fast_extra_smem(int n_in, bool has_pw) {
+    return (size_t)kChunk * n_in * 4 + (has_pw ? (size_t)kChunk * 4 : 0) + 32 * kQueueCap * 4 + 64;
+}
+
+template <int N_IN, bool HAS_PW>
+__global__ void __launch_bounds__(1024, 1)
+fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict__ rotation,
+                       const float* __restrict__ translation, const float* __restrict__ background,
+                       const float* __restrict__ out_weight, const float* __restrict__ point_weight,
+                       float* __restrict__ out, Grid<float, 2> grid, int P, FastTileParams tp) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ long long scratch[32];
+    const int per_pose = tp.slabs * tp.splits;
+    const int64_t b = blockIdx.x / per_pose;
+    const int rem = blockIdx.x % per_pose;
+    const int s = rem / tp.splits, q = rem % tp.splits;
+    const int g0 = grid.g[0], g1 = grid.g[1];
+    const int ys = tp.band_lo + s * tp.rows;
+    const int ye = (ys + tp.rows < tp.band_hi) ? ys + tp.rows : tp.band_hi;
+    const int nrows = ye - ys;
+    const int n_tile = nrows * g0;
+    const int tile_cap = tp.rows * g0;                       // carve-up is the same for every CTA of the launch
+    unsigned* tile_u = reinterpret_cast<unsigned*>(smem_raw);
+    float* tile_f = reinterpret_cast<float*>(smem_raw);
+    unsigned char* after = smem_raw + (((size_t)tile_cap * 4 + 127) / 128) * 128;
+    float* stage_pts = reinterpret_cast<float*>(after);
+    float* stage_pw = stage_pts + kChunk * N_IN;
+    int* queue = reinterpret_cast<int*>(stage_pw + (HAS_PW ? kChunk : 0));
+    uint64_t* bars = reinterpret_cast<uint64_t*>(queue + 32 * kQueueCap);   // [0] full, [1] empty
+    float* __restrict__ img = out + b * grid.cells;
+    const float bg = background ? __ldg(background + b) : 0.f;
+    const bool border = (tp.band_lo > 0 || tp.band_hi < g1);
+    const bool do_border = border && s == 0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int* wq = queue + warp * kQueueCap;
+
+    Pose<float, N_IN, 2> pose;
+    load_pose(pose, rotation, translation, out_weight, b);
+    const int p_begin = q * tp.per_split;
+    const int p_end = (p_begin + tp.per_split < P) ? p_begin + tp.per_split : P;
+
+    // fixed-point scale (uniform across the CTA); not eligible -> float CAS accumulation through the generic code
+    bool fixed = false;
+    float qscale = 0.f, inv_qscale = 0.f;
+    {
+        float cmax = pose.ow;
+        bool ok = cmax > 0.f;
+        if (HAS_PW) {
+            const float wmax = __ldg(tp.pw_stats), wmin = __ldg(tp.pw_stats + 1), wmean = __ldg(tp.pw_stats + 2);
+            ok = ok && wmin >= 0.f && wmax > 0.f && wmax <= 64.f * wmean;
+            cmax *= wmax;
+        }
+        ok = ok && cmax > 1e-30f && cmax < 1e30f;
+        if (ok) {
+            int e;
+            frexpf(cmax, &e);                                  // cmax <= 2^e
+            qscale = ldexpf(1.0f, tp.fixed_bits - e);
+            inv_qscale = ldexpf(1.0f, e - tp.fixed_bits);
+            fixed = true;
+        }
+    }
+
+    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile_u[i] = 0u;
+    if (tp.exclusive && border) {
+        const int lo_cells = tp.band_lo * g0;
+        for (int i = threadIdx.x; i < lo_cells; i += blockDim.x) img[i] = bg;
+        for (int i = tp.band_hi * g0 + threadIdx.x; i < g0 * g1; i += blockDim.x) img[i] = bg;
+        __threadfence();
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], blockDim.x >> 5);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    long long mass = 0;
+    if (fixed) {
+        // ---- packed pose registers ------------------------------------------------------------------------
+        float2 Rj[N_IN];
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) Rj[j] = make_float2(pose.R[0][j], pose.R[1][j]);
+        const float2 neg_origin = make_float2(-pose.origin[0], -pose.origin[1]);   // proj - origin == proj + (-origin)
+        const float2 scale2 = make_float2(grid.scale[0], grid.scale[1]);
+        const float wq_pose = pose.ow * qscale;
+        const float magic_hi = kMagic;
+        unsigned mass32 = 0;
+        int wq_count = 0;                                   // warp-uniform
+
+        // quantised add of one corner into the tile
+        auto tile_add = [&](int off, float v_times_q) {
+            const int qv = __float_as_int(v_times_q + magic_hi) - kMagicBits;
+            atomicAdd(tile_u + off, (unsigned)qv);
+            mass32 += (unsigned)qv;
+        };
+        // generic (any position) handling of one point: used for the deferred lanes
+        auto slow_point = [&](int p) {
+            float x[N_IN];
+            load_point(x, points, (int64_t)p);
+            int i0[2];
+            float dl[2];
+            if (!stencil(x, pose, grid, i0, dl)) return;
+            const float pw = HAS_PW ? __ldg(point_weight + p) : 1.f;
+            const float weight = pose.ow * pw;
+            const float du0 = 1.f - dl[0], du1 = 1.f - dl[1];
+            const float w[4] = {du0 * du1, dl[0] * du1, du0 * dl[1], dl[0] * dl[1]};
+            const bool x_lo = i0[0] >= 0, x_hi = i0[0] + 1 < g0;
+#pragma unroll
+            for (int cy = 0; cy < 2; ++cy) {
+                const int iy = i0[1] + cy;
+                if (iy < 0 || iy >= g1) continue;
+                if (iy >= ys && iy < ye) {
+                    const int off = (iy - ys) * g0 + i0[0];
+                    if (x_lo) tile_add(off, (w[2 * cy] * weight) * qscale);
+                    if (x_hi) tile_add(off + 1, (w[2 * cy + 1] * weight) * qscale);
+                } else if (do_border && (iy < tp.band_lo || iy >= tp.band_hi)) {
+                    float* addr = img + (int64_t)iy * g0 + i0[0];
+                    const float va = w[2 * cy] * weight, vb = w[2 * cy + 1] * weight;
+                    if (x_lo && x_hi) red_add2(addr, va, vb);
+                    else if (x_lo) red_add(addr, va);
+                    else if (x_hi) red_add(addr + 1, vb);
+                }
+            }
+        };
+
+        const int n_chunks = (p_end - p_begin + kChunk - 1) / kChunk;
+        auto issue_chunk = [&](int c) {   // thread 0 only
+            const int c0 = p_begin + c * kChunk;
+            const int n = (p_end - c0 < kChunk) ? p_end - c0 : kChunk;
+            const uint32_t bytes_pts = (uint32_t)n * N_IN * 4, bytes_pw = (uint32_t)n * 4;
+            const uint32_t b16_pts = bytes_pts & ~15u, b16_pw = HAS_PW ? (bytes_pw & ~15u) : 0u;
+            // tails (< 16 bytes) that the bulk copy cannot move
+            for (uint32_t i = b16_pts / 4; i < bytes_pts / 4; ++i) stage_pts[i] = __ldg(points + (int64_t)c0 * N_IN + i);
+            if (HAS_PW) for (uint32_t i = b16_pw / 4; i < bytes_pw / 4; ++i) stage_pw[i] = __ldg(point_weight + c0 + i);
+            mbar_arrive_expect_tx(&bars[0], b16_pts + b16_pw);
+            if (b16_pts) tma_load_1d(stage_pts, points + (int64_t)c0 * N_IN, b16_pts, &bars[0]);
+            if (HAS_PW && b16_pw) tma_load_1d(stage_pw, point_weight + c0, b16_pw, &bars[0]);
+        };
+        if (threadIdx.x == 0 && n_chunks > 0) issue_chunk(0);
+
+        for (int c = 0; c < n_chunks; ++c) {
+            const int c0 = p_begin + c * kChunk;
+            const int n = (p_end - c0 < kChunk) ? p_end - c0 : kChunk;
+            const bool active = (int)threadIdx.x < n;
+            mbar_wait(&bars[0], c & 1);
+            float x[N_IN], pw = 1.f;
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) x[j] = stage_pts[threadIdx.x * N_IN + j];
+            if (HAS_PW) pw = stage_pw[threadIdx.x];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&bars[1]);
+            if (threadIdx.x == 0 && c + 1 < n_chunks) {
+                mbar_wait(&bars[1], c & 1);   // every warp has its chunk-c points in registers
+                issue_chunk(c + 1);
+            }
+
+            // ---- transform + stencil, both output dimensions packed (src/raster.jl:88-99) -------------------
+            // ptxas 12.9 contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even though both carry .rn (and even with
+            // -fmad=false), which would change the last bit of `coord` and flip cells.  Scalar add.rn.f32 IS respected,
+            // so: products packed (FMUL2), every add that consumes a product scalar (FADD), the rest packed.
+            // tests/test_abi.py asserts that this kernel contains no FFMA2 at all.
+            float2 prod[N_IN];
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) prod[j] = __fmul2_rn(Rj[j], make_float2(x[j], x[j]));
+            float s0 = prod[0].x, s1 = prod[0].y;
+#pragma unroll
+            for (int j = 1; j < N_IN; ++j) { s0 = __fadd_rn(s0, prod[j].x); s1 = __fadd_rn(s1, prod[j].y); }
+            const float2 coord = __fmul2_rn(__fadd2_rn(make_float2(s0, s1), neg_origin), scale2);
+            const float2 r = make_float2(ceilf(__fadd_rn(coord.x, -0.5f)), ceilf(__fadd_rn(coord.y, -0.5f)));
+            const float2 t = __fadd2_rn(r, make_float2(-0.5f, -0.5f));
+            const float2 dl = make_float2(__fsub_rn(coord.x, t.x), __fsub_rn(coord.y, t.y));   // coord - (r - 0.5)
+            const float2 du = __fadd2_rn(make_float2(1.f, 1.f), make_float2(-dl.x, -dl.y));
+            const int ix = __float2int_rn(r.x) - 1, iy = __float2int_rn(r.y) - 1;
+            const int ry = iy - ys;
+            const bool interior = active && (unsigned)ix < (unsigned)(g0 - 1) && (unsigned)ry < (unsigned)(nrows - 1);
+            if (interior) {
+                const float wq = HAS_PW ? wq_pose * pw : wq_pose;
+                const float a = du.y * wq, bq = dl.y * wq;
+                const int off = ry * g0 + ix;
+                tile_add(off, du.x * a);
+                tile_add(off + 1, dl.x * a);
+                tile_add(off + g0, du.x * bq);
+                tile_add(off + g0 + 1, dl.x * bq);
+            }
+            // ---- defer the lanes that are not interior but touch this CTA's cells (warp-level compaction) ------
+            const bool touches_slab = (unsigned)(ry + 1) < (unsigned)(nrows + 1);
+            const bool touches_border = do_border && (iy < tp.band_lo || iy + 1 >= tp.band_hi);
+            const bool slow = active && !interior && (touches_slab || touches_border);
+            const unsigned slow_mask = __ballot_sync(0xffffffffu, slow);
+            if (slow_mask) {
+                if (slow) wq[wq_count + __popc(slow_mask & ((1u << lane) - 1u))] = c0 + (int)threadIdx.x;
+                wq_count += __popc(slow_mask);
+                __syncwarp();
+                if (wq_count >= 32) {
+                    slow_point(wq[wq_count - 32 + lane]);
+                    wq_count -= 32;
+                    __syncwarp();
+                }
+            }
+            if ((c & 63) == 63) { mass += mass32; mass32 = 0; }
+        }
+        if (lane < wq_count) slow_point(wq[lane]);
+        mass += mass32;
+
+        mass = block_sum_ll(mass, scratch);          // contains the __syncthreads that ends the accumulation
+        long long cells_sum = 0;
+        for (int i = threadIdx.x; i < n_tile; i += blockDim.x) cells_sum += (long long)tile_u[i];
+        cells_sum = block_sum_ll(cells_sum, scratch);
+        if (cells_sum != mass) {
+            // a 32-bit cell wrapped: redo this slab in float (border splats were already sent)
+            fixed = false;
+            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile_f[i] = 0.f;
+            __syncthreads();
+            tile_accumulate<float, N_IN, false>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
+                                                tp.band_lo, tp.band_hi, false, 0.f);
+            __syncthreads();
+        }
+    } else {
+        tile_accumulate<float, N_IN, false>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
+                                            tp.band_lo, tp.band_hi, do_border, 0.f);
+        __syncthreads();
+    }
+
+    auto cell_value = [&](int i) -> float { return fixed ? (float)tile_u[i] * inv_qscale : tile_f[i]; };
+    float* __restrict__ dst = img + (int64_t)ys * g0;
+    if (tp.exclusive) {
+        if ((n_tile & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            for (int i = threadIdx.x; i < n_tile / 4; i += blockDim.x) {
+                float4 v;
+                v.x = cell_value(4 * i) + bg;
+                v.y = cell_value(4 * i + 1) + bg;
+                v.z = cell_value(4 * i + 2) + bg;
+                v.w = cell_value(4 * i + 3) + bg;
+                reinterpret_cast<float4*>(dst)[i] = v;
+            }
+        } else {
+            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) dst[i] = cell_value(i) + bg;
+        }
+    } else {
+        for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
+            const float v = cell_value(i);
+            if (v != 0.f) red_add(dst + i, v);
+        }
+    }
+}
+
+}  // namespace dpr

@@ -66,7 +66,7 @@ pullback_gather_global_kernel(const T* __restrict__ ds_dout, const T* __restrict
                               T* __restrict__ d_out_weight, T* __restrict__ d_point_weight, Grid<T, N_OUT> grid,
                               int64_t P, int64_t B, int point_chunks, int pose_chunk) {
     constexpr int NV = PoseGradLayout<N_IN, N_OUT>::NV;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* pose_acc = reinterpret_cast<T*>(smem_raw);  // [pose_chunk][NV]
 
     const int pc = blockIdx.x % point_chunks;

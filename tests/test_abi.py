@@ -35,6 +35,21 @@ def test_library_is_sm100a_only():
         assert "sm_100a" in out and "sm_90" not in out and "sm_80" not in out
 
 
+def test_fast_forward_kernel_has_no_packed_fma():
+    """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (illegal for .rn, ignores -fmad=false); the cell a
+    point lands in depends on the last bit of `coord`, so the fast forward kernel is written so that no such pair
+    exists.  Guard: its SASS must not contain a single FFMA2, and must contain the packed multiplies and the TMA copy."""
+    sass = os.popen(f"cuobjdump -sass {_lib.LIB_PATH} 2>/dev/null").read()
+    if not sass.strip():
+        pytest.skip("cuobjdump not available")
+    chunks = sass.split("Function : ")
+    fast = [c for c in chunks if "fwd_tile2d_fast_kernel" in c.split("\n", 1)[0]]
+    assert len(fast) == 4, "expected 4 instantiations of the fast forward kernel"
+    for body in fast:
+        assert "FFMA2" not in body
+        assert "FMUL2" in body and "UBLKCP" in body and "ATOMS.ADD" in body
+
+
 def test_status_strings_and_options():
     lib = _lib.load()
     assert lib.dpr_version() >= 100
