@@ -3,9 +3,10 @@
 // Same decomposition as fwd_splat_tile2d_kernel (CTA = pose x slab x point split, slab accumulated in shared
 // memory, one coalesced flush), with the inner loop rebuilt around what the ncu captures of that kernel showed
 // (profiles/): it was bound by issue slots, not by memory.
-//   * points arrive through TMA: one elected thread issues cp.async.bulk (UBLKCP) per 1024-point chunk into a
-//     shared-memory stage guarded by a full/empty mbarrier pair; every thread then reads its point with three
-//     conflict-free LDS instead of three strided LDG (which cost 3x the L2 sectors with no L1 left beside the tile);
+//   * the next chunk's point is prefetched into registers while the current one is processed (a TMA-staged variant,
+//     cp.async.bulk per 1024-point chunk behind a full/empty mbarrier pair, measured SLOWER - 3.03 ms vs 2.03 ms on
+//     config 2 - because one shared stage forces the 32 warps into lock-step and exposes the copy latency, while a
+//     second stage costs 12 rows of tile; the mbarrier/TMA helpers below are kept for the pullback's image staging);
 //   * the transform and the stencil run on Blackwell's packed FP32x2 pipe (FMUL2/FADD2/FFMA2: both output
 //     dimensions in one instruction), still unfused and in the reference's operation order, so cell assignment is
 //     bit-identical to the scalar path (dpr_common.cuh::stencil);
@@ -57,7 +58,8 @@ struct FastTileParams {
 
 // shared-memory carve-up (bytes) after the tile
 __host__ __device__ inline size_t fast_extra_smem(int n_in, bool has_pw) {
-    return (size_t)kChunk * n_in * 4 + (has_pw ? (size_t)kChunk * 4 : 0) + 32 * kQueueCap * 4 + 64;
+    (void)n_in; (void)has_pw;
+    return (size_t)32 * kQueueCap * 4;
 }
 
 template <int N_IN, bool HAS_PW>
@@ -81,10 +83,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
     unsigned* tile_u = reinterpret_cast<unsigned*>(smem_raw);
     float* tile_f = reinterpret_cast<float*>(smem_raw);
     unsigned char* after = smem_raw + (((size_t)tile_cap * 4 + 127) / 128) * 128;
-    float* stage_pts = reinterpret_cast<float*>(after);
-    float* stage_pw = stage_pts + kChunk * N_IN;
-    int* queue = reinterpret_cast<int*>(stage_pw + (HAS_PW ? kChunk : 0));
-    uint64_t* bars = reinterpret_cast<uint64_t*>(queue + 32 * kQueueCap);   // [0] full, [1] empty
+    int* queue = reinterpret_cast<int*>(after);
     float* __restrict__ img = out + b * grid.cells;
     const float bg = background ? __ldg(background + b) : 0.f;
     const bool border = (tp.band_lo > 0 || tp.band_hi < g1);
@@ -124,11 +123,6 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         for (int i = threadIdx.x; i < lo_cells; i += blockDim.x) img[i] = bg;
         for (int i = tp.band_hi * g0 + threadIdx.x; i < g0 * g1; i += blockDim.x) img[i] = bg;
         __threadfence();
-    }
-    if (threadIdx.x == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], blockDim.x >> 5);
-        mbar_fence_init();
     }
     __syncthreads();
 
@@ -182,34 +176,28 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         };
 
         const int n_chunks = (p_end - p_begin + kChunk - 1) / kChunk;
-        auto issue_chunk = [&](int c) {   // thread 0 only
-            const int c0 = p_begin + c * kChunk;
-            const int n = (p_end - c0 < kChunk) ? p_end - c0 : kChunk;
-            const uint32_t bytes_pts = (uint32_t)n * N_IN * 4, bytes_pw = (uint32_t)n * 4;
-            const uint32_t b16_pts = bytes_pts & ~15u, b16_pw = HAS_PW ? (bytes_pw & ~15u) : 0u;
-            // tails (< 16 bytes) that the bulk copy cannot move
-            for (uint32_t i = b16_pts / 4; i < bytes_pts / 4; ++i) stage_pts[i] = __ldg(points + (int64_t)c0 * N_IN + i);
-            if (HAS_PW) for (uint32_t i = b16_pw / 4; i < bytes_pw / 4; ++i) stage_pw[i] = __ldg(point_weight + c0 + i);
-            mbar_arrive_expect_tx(&bars[0], b16_pts + b16_pw);
-            if (b16_pts) tma_load_1d(stage_pts, points + (int64_t)c0 * N_IN, b16_pts, &bars[0]);
-            if (HAS_PW && b16_pw) tma_load_1d(stage_pw, point_weight + c0, b16_pw, &bars[0]);
-        };
-        if (threadIdx.x == 0 && n_chunks > 0) issue_chunk(0);
-
+        // software pipeline: the point of the next chunk is loaded while the current one is processed
+        float xn[N_IN], pwn = 1.f;
+        {
+            const int p0 = p_begin + (int)threadIdx.x;
+            if (p0 < p_end) {
+                load_point(xn, points, (int64_t)p0);
+                if (HAS_PW) pwn = __ldg(point_weight + p0);
+            }
+        }
         for (int c = 0; c < n_chunks; ++c) {
             const int c0 = p_begin + c * kChunk;
-            const int n = (p_end - c0 < kChunk) ? p_end - c0 : kChunk;
-            const bool active = (int)threadIdx.x < n;
-            mbar_wait(&bars[0], c & 1);
-            float x[N_IN], pw = 1.f;
+            const bool active = c0 + (int)threadIdx.x < p_end;
+            float x[N_IN];
 #pragma unroll
-            for (int j = 0; j < N_IN; ++j) x[j] = stage_pts[threadIdx.x * N_IN + j];
-            if (HAS_PW) pw = stage_pw[threadIdx.x];
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&bars[1]);
-            if (threadIdx.x == 0 && c + 1 < n_chunks) {
-                mbar_wait(&bars[1], c & 1);   // every warp has its chunk-c points in registers
-                issue_chunk(c + 1);
+            for (int j = 0; j < N_IN; ++j) x[j] = xn[j];
+            const float pw = pwn;
+            {
+                const int pn = c0 + kChunk + (int)threadIdx.x;
+                if (pn < p_end) {
+                    load_point(xn, points, (int64_t)pn);
+                    if (HAS_PW) pwn = __ldg(point_weight + pn);
+                }
             }
 
             // ---- transform + stencil, both output dimensions packed (src/raster.jl:88-99) -------------------

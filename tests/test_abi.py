@@ -38,7 +38,7 @@ def test_library_is_sm100a_only():
 def test_fast_forward_kernel_has_no_packed_fma():
     """ptxas 12.9 fuses mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (illegal for .rn, ignores -fmad=false); the cell a
     point lands in depends on the last bit of `coord`, so the fast forward kernel is written so that no such pair
-    exists.  Guard: its SASS must not contain a single FFMA2, and must contain the packed multiplies and the TMA copy."""
+    exists.  Guard: its SASS must not contain a single FFMA2, and must contain the packed multiplies and native ATOMS."""
     sass = os.popen(f"cuobjdump -sass {_lib.LIB_PATH} 2>/dev/null").read()
     if not sass.strip():
         pytest.skip("cuobjdump not available")
@@ -47,7 +47,7 @@ def test_fast_forward_kernel_has_no_packed_fma():
     assert len(fast) == 4, "expected 4 instantiations of the fast forward kernel"
     for body in fast:
         assert "FFMA2" not in body
-        assert "FMUL2" in body and "UBLKCP" in body and "ATOMS.ADD" in body
+        assert "FMUL2" in body and "ATOMS.ADD" in body
 
 
 def test_status_strings_and_options():
