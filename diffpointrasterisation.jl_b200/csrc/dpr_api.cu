@@ -28,11 +28,11 @@ static std::atomic<int> g_prof_on{0};
 LaunchScope::LaunchScope(const char* n, cudaStream_t s) : name(n), stream(s), slot(-1) {
     count_launches(1);
     if (!g_prof_on.load(std::memory_order_relaxed)) return;
-    ProfileRecord r{n, nullptr, nullptr};
-    if (cudaEventCreate(&r.e0) != cudaSuccess || cudaEventCreate(&r.e1) != cudaSuccess) return;
-    cudaEventRecord(r.e0, s);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (cudaEventCreate(&e0) != cudaSuccess || cudaEventCreate(&e1) != cudaSuccess) return;
+    cudaEventRecord(e0, s);
     std::lock_guard<std::mutex> lock(g_prof_mutex);
-    g_prof.push_back(r);
+    g_prof.emplace_back(ProfileRecord{n, e0, e1});
     slot = (int)g_prof.size() - 1;
 }
 LaunchScope::~LaunchScope() {

@@ -262,8 +262,74 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     return DPR_OK;
 }
 
+}  // namespace dpr
+#include "dpr_pullback_fast.cuh"
+namespace dpr {
+
+// zero everything that is accumulated with REDG (ext/DiffPointRasterisationCUDAExt.jl:272-276)
+template <typename T>
+static int zero_gradients(const PullbackArgs<T>& a) {
+    const int nr = a.n_in * a.n_out;
+    DPR_CUDA_TRY(cudaMemsetAsync(a.d_points, 0, sizeof(T) * (size_t)(a.P * a.n_in), a.stream));
+    DPR_CUDA_TRY(cudaMemsetAsync(a.d_rotation, 0, sizeof(T) * (size_t)(a.B * nr), a.stream));
+    DPR_CUDA_TRY(cudaMemsetAsync(a.d_translation, 0, sizeof(T) * (size_t)(a.B * a.n_out), a.stream));
+    if (a.d_out_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_out_weight, 0, sizeof(T) * (size_t)a.B, a.stream));
+    if (a.d_point_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_point_weight, 0, sizeof(T) * (size_t)a.P, a.stream));
+    return DPR_OK;
+}
+
+template <typename T, int N_IN>
+static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
+    constexpr int K = 4;
+    constexpr int NV = 2 * N_IN + 3, PP = (NV + 3) / 4 * 4;
+    Grid<T, 2> grid;
+    grid.cells = 1;
+    for (int k = 0; k < 2; ++k) {
+        grid.g[k] = (int)a.grid[k];
+        grid.scale[k] = T(a.grid[k]) / T(2);  // src/raster_pullback.jl:29
+        grid.cells *= a.grid[k];
+    }
+    int rc = zero_gradients(a);
+    if (rc != DPR_OK) return rc;
+    rc = launch_background_sum(a, grid.cells, dev);
+    if (rc != DPR_OK) return rc;
+    if (a.P == 0 || a.B == 0) return DPR_OK;
+    const int threads = 256;
+    const int64_t point_chunks = (a.P + (int64_t)threads * K - 1) / ((int64_t)threads * K);
+    int64_t pose_chunk = tuning().pose_chunk;
+    if (pose_chunk <= 0) {
+        const int64_t want_ctas = (int64_t)dev.sm_count * 8 * 4;
+        int64_t pose_chunks = (want_ctas + point_chunks - 1) / point_chunks;
+        if (pose_chunks < 1) pose_chunks = 1;
+        if (pose_chunks > a.B) pose_chunks = a.B;
+        pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
+        if (pose_chunk < 8) pose_chunk = a.B < 8 ? a.B : 8;
+    }
+    if (pose_chunk > 512) pose_chunk = 512;
+    if (pose_chunk > a.B) pose_chunk = a.B;
+    const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
+    if (point_chunks * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
+    const size_t smem = sizeof(T) * (size_t)pose_chunk * (PP + NV);
+    auto launch = [&](auto kern) -> int {
+        LaunchScope scope("pullback_gather2d", a.stream);
+        kern<<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
+            a.ds_dout, a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.d_points, a.d_rotation,
+            a.d_translation, a.d_out_weight, a.d_point_weight, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
+        return DPR_OK;
+    };
+    rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true>) : launch(pullback_gather2d_kernel<T, N_IN, K, false>);
+    if (rc != DPR_OK) return rc;
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_PULLBACK, "gather2d");
+    return DPR_OK;
+}
+
 template <typename T>
 int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
+    if (a.n_out == 2 && tuning().pullback_algo != 1 && a.P < (int64_t)0x3fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff) {
+        if (a.n_in == 2) return pullback_gather2d<T, 2>(a, dev);
+        if (a.n_in == 3) return pullback_gather2d<T, 3>(a, dev);
+    }
     if (a.n_in == 2 && a.n_out == 2) return pullback_global<T, 2, 2>(a, dev);
     if (a.n_in == 3 && a.n_out == 2) return pullback_global<T, 3, 2>(a, dev);
     if (a.n_in == 3 && a.n_out == 3) return pullback_global<T, 3, 3>(a, dev);

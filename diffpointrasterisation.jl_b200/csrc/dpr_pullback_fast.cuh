@@ -1,0 +1,221 @@
+// dpr_pullback_fast.cuh - 2-d pullback kernel (gathers from global memory / L2), included by dpr_pullback.cu.
+//
+// Same decomposition as pullback_gather_global_kernel (a thread owns K points and loops over its CTA's pose chunk),
+// rebuilt after the first ncu capture (profiles/ncu_full_r01_v1_summary.csv: 194 instructions per warp-splat, LSU
+// data pipe 80 % busy, issue slots 55 %):
+//   * pose parameters of the chunk are staged once in shared memory and read back with broadcast LDS.128;
+//   * the stencil runs on the packed FP32x2 pipe where that is safe (see the ptxas note in dpr_forward_fast.cuh);
+//   * the four corners are fetched with predicated loads from one base address - no per-corner branches;
+//   * the per-pose reduction of the 2*N_in+3 point-sums uses a transposing butterfly (each shuffle step halves the
+//     number of live values) instead of one 5-step shuffle tree per value.
+#pragma once
+#include <type_traits>
+
+#include "dpr_common.cuh"
+
+namespace dpr {
+
+// Sum 8 values across the warp.  On return lane L (with (L & 3) == 0) holds the total of value index
+// v = 4*bit4(L) + 2*bit3(L) + bit2(L) in a[0].
+template <typename T>
+__device__ __forceinline__ void butterfly8(T (&a)[8], int lane) {
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const T send = h16 ? a[i] : a[i + 4];
+        const T keep = h16 ? a[i + 4] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const T send = h8 ? a[i] : a[i + 2];
+        const T keep = h8 ? a[i + 2] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    {
+        const T send = h4 ? a[0] : a[1];
+        const T keep = h4 ? a[1] : a[0];
+        a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 2);
+    a[0] += __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
+
+// lower-corner cell (0-based) and dl for the 2-d case, bit-identical to dpr_common.cuh::stencil.
+// Non-finite or far-away coordinates give indices for which every corner predicate below is false.
+template <typename T, int N_IN>
+__device__ __forceinline__ void stencil2(const T (&x)[N_IN], const T (&R)[2][N_IN], const T (&neg_origin)[2],
+                                         const T (&scale)[2], const int (&g)[2], int& ix, int& iy, T (&dl)[2]) {
+    T r[2];
+    if constexpr (std::is_same<T, float>::value) {
+        float2 prod[N_IN];
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) prod[j] = __fmul2_rn(make_float2(R[0][j], R[1][j]), make_float2(x[j], x[j]));
+        float s0 = prod[0].x, s1 = prod[0].y;
+#pragma unroll
+        for (int j = 1; j < N_IN; ++j) { s0 = __fadd_rn(s0, prod[j].x); s1 = __fadd_rn(s1, prod[j].y); }
+        const float2 coord = __fmul2_rn(__fadd2_rn(make_float2(s0, s1), make_float2(neg_origin[0], neg_origin[1])),
+                                        make_float2(scale[0], scale[1]));
+        r[0] = ceilf(__fadd_rn(coord.x, -0.5f));
+        r[1] = ceilf(__fadd_rn(coord.y, -0.5f));
+        const float2 t = __fadd2_rn(make_float2(r[0], r[1]), make_float2(-0.5f, -0.5f));
+        dl[0] = __fsub_rn(coord.x, t.x);
+        dl[1] = __fsub_rn(coord.y, t.y);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            T proj = mul_rn(R[k][0], x[0]);
+#pragma unroll
+            for (int j = 1; j < N_IN; ++j) proj = add_rn(proj, mul_rn(R[k][j], x[j]));
+            const T coord = mul_rn(add_rn(proj, neg_origin[k]), scale[k]);
+            r[k] = ceil_t(sub_rn(coord, T(0.5)));
+            dl[k] = sub_rn(coord, sub_rn(r[k], T(0.5)));
+        }
+    }
+    // clamp in floating point first: NaN -> -2, huge -> g+2, so the integer conversion is always safe
+    const T rx = fmin(fmax(r[0], T(-2)), T(g[0] + 2)), ry = fmin(fmax(r[1], T(-2)), T(g[1] + 2));
+    ix = to_int_sat(rx) - 1;
+    iy = to_int_sat(ry) - 1;
+}
+
+template <typename T, int N_IN, int K, bool HAS_PW>
+__global__ void __launch_bounds__(256)
+pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ points, const T* __restrict__ rotation,
+                         const T* __restrict__ translation, const T* __restrict__ out_weight,
+                         const T* __restrict__ point_weight, T* __restrict__ d_points, T* __restrict__ d_rotation,
+                         T* __restrict__ d_translation, T* __restrict__ d_out_weight, T* __restrict__ d_point_weight,
+                         Grid<T, 2> grid, int P, int64_t B, int point_chunks, int pose_chunk) {
+    constexpr int NR = 2 * N_IN;            // rotation entries
+    constexpr int NV = NR + 3;              // + translation (2) + out_weight
+    constexpr int PP = (NV + 3) / 4 * 4;    // padded pose-parameter record: R (col-major), -origin (2), ow
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* pose_par = reinterpret_cast<T*>(smem_raw);              // [pose_chunk][PP]
+    T* pose_acc = pose_par + (size_t)pose_chunk * PP;          // [pose_chunk][NV]
+
+    const int pc = blockIdx.x % point_chunks;
+    const int64_t bc = blockIdx.x / point_chunks;
+    const int64_t b0 = bc * pose_chunk;
+    const int n_pose = (int)((b0 + pose_chunk < B ? b0 + pose_chunk : B) - b0);
+    for (int i = threadIdx.x; i < n_pose * PP; i += blockDim.x) {
+        const int bl = i / PP, v = i % PP;
+        const int64_t b = b0 + bl;
+        T val = T(0);
+        if (v < NR) val = __ldg(rotation + b * NR + v);
+        else if (v < NR + 2) val = -sub_rn(T(-1), __ldg(translation + b * 2 + (v - NR)));   // -origin, origin = -1 - t
+        else if (v == NR + 2) val = out_weight ? __ldg(out_weight + b) : T(1);
+        pose_par[i] = val;
+    }
+    for (int i = threadIdx.x; i < n_pose * NV; i += blockDim.x) pose_acc[i] = T(0);
+    __syncthreads();
+
+    T x[K][N_IN], pw[K], dpt[K][N_IN], dpw[K];
+    bool valid[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = (pc * K + k) * (int)blockDim.x + (int)threadIdx.x;
+        valid[k] = p < P;
+        const int pp = valid[k] ? p : 0;
+        load_point(x[k], points, (int64_t)pp);
+        pw[k] = HAS_PW ? __ldg(point_weight + pp) : T(1);
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) dpt[k][j] = T(0);
+        dpw[k] = T(0);
+    }
+    const int g[2] = {grid.g[0], grid.g[1]};
+    const T scale[2] = {grid.scale[0], grid.scale[1]};
+    const int lane = threadIdx.x & 31;
+    const int vsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+
+    for (int bl = 0; bl < n_pose; ++bl) {
+        T par[PP];
+        if constexpr (std::is_same<T, float>::value) {
+#pragma unroll
+            for (int i = 0; i < PP / 4; ++i) {
+                const float4 q = reinterpret_cast<const float4*>(pose_par + bl * PP)[i];
+                par[4 * i] = q.x; par[4 * i + 1] = q.y; par[4 * i + 2] = q.z; par[4 * i + 3] = q.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < PP / 2; ++i) {
+                const double2 q = reinterpret_cast<const double2*>(pose_par + bl * PP)[i];
+                par[2 * i] = q.x; par[2 * i + 1] = q.y;
+            }
+        }
+        T R[2][N_IN];
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) { R[0][j] = par[2 * j]; R[1][j] = par[2 * j + 1]; }
+        const T neg_origin[2] = {par[NR], par[NR + 1]};
+        const T ow = par[NR + 2];
+        const T* __restrict__ img = ds_dout + (b0 + bl) * grid.cells;
+
+        T acc[8], acc_ow = T(0);    // acc: d_rotation (col-major, NR values), d_translation (2) [, padding]
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[v] = T(0);
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            int ix, iy;
+            T dl[2];
+            stencil2<T, N_IN>(x[k], R, neg_origin, scale, g, ix, iy, dl);
+            // per-corner bounds rule (src/raster_pullback.jl:51) as four load predicates
+            const bool x_lo = valid[k] && (unsigned)ix < (unsigned)g[0], x_hi = valid[k] && (unsigned)(ix + 1) < (unsigned)g[0];
+            const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
+            const T* base = img + ((int64_t)iy * g[0] + ix);
+            T G00 = T(0), G10 = T(0), G01 = T(0), G11 = T(0);
+            if (x_lo && y_lo) G00 = __ldg(base);
+            if (x_hi && y_lo) G10 = __ldg(base + 1);
+            if (x_lo && y_hi) G01 = __ldg(base + g[0]);
+            if (x_hi && y_hi) G11 = __ldg(base + g[0] + 1);
+            const T du0 = T(1) - dl[0], du1 = T(1) - dl[1];
+            // s = sum_c W_c G_c; gx, gy = d/dcoord (differences first: no cancellation against the oracle's f64 sums)
+            const T s = du1 * (du0 * G00 + dl[0] * G10) + dl[1] * (du0 * G01 + dl[0] * G11);
+            const T gx = du1 * (G10 - G00) + dl[1] * (G11 - G01);
+            const T gy = du0 * (G01 - G00) + dl[0] * (G11 - G10);
+            acc_ow += HAS_PW ? s * pw[k] : s;                 // src/raster_pullback.jl:57
+            dpw[k] += s * ow;                                  // :58
+            const T f = HAS_PW ? ow * pw[k] : ow;              // :60
+            const T sx = (f * gx) * scale[0], sy = (f * gy) * scale[1];   // :67
+            if constexpr (N_IN == 3) {
+                acc[6] += sx; acc[7] += sy;                    // :68
+            } else {
+                acc[4] += sx; acc[5] += sy;
+            }
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) {
+                acc[2 * j] += sx * x[k][j];                    // :69
+                acc[2 * j + 1] += sy * x[k][j];
+                dpt[k][j] += R[0][j] * sx + R[1][j] * sy;      // :70-71
+            }
+        }
+        if constexpr (N_IN == 2) acc[6] = acc_ow;              // 7 values fit the butterfly
+        butterfly8(acc, lane);
+        if constexpr (N_IN == 3) acc_ow = warp_sum(acc_ow);
+        if ((lane & 3) == 0) {
+            // butterfly slot -> (rotation entries | translation | out_weight) slot of pose_acc
+            const int slot = vsel;   // N_IN==3: 0..5 rotation, 6..7 translation; N_IN==2: 0..3 rot, 4..5 trans, 6 ow
+            if (slot < NV) atomicAdd(&pose_acc[bl * NV + slot], acc[0]);
+        }
+        if constexpr (N_IN == 3) {
+            if (lane == 1) atomicAdd(&pose_acc[bl * NV + NV - 1], acc_ow);
+        }
+    }
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        if (!valid[k]) continue;
+        const int p = (pc * K + k) * (int)blockDim.x + (int)threadIdx.x;
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) red_add(d_points + (int64_t)p * N_IN + j, dpt[k][j]);
+        if (d_point_weight) red_add(d_point_weight + p, dpw[k]);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_pose * NV; i += blockDim.x) {
+        const int bl = i / NV, v = i % NV;
+        const T r = pose_acc[i];
+        const int64_t b = b0 + bl;
+        if (v < NR) red_add(d_rotation + b * NR + v, r);
+        else if (v < NR + 2) red_add(d_translation + b * 2 + (v - NR), r);
+        else if (d_out_weight) red_add(d_out_weight + b, r);
+    }
+}
+
+}  // namespace dpr

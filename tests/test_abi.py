@@ -48,6 +48,10 @@ def test_fast_forward_kernel_has_no_packed_fma():
     for body in fast:
         assert "FFMA2" not in body
         assert "FMUL2" in body and "ATOMS.ADD" in body
+    pb = [c for c in chunks if "pullback_gather2d_kernelIf" in c.split("\n", 1)[0]]
+    assert len(pb) == 4
+    for body in pb:
+        assert "FFMA2" not in body and "FMUL2" in body
 
 
 def test_status_strings_and_options():

@@ -149,14 +149,34 @@ def test_forward_fixed_point_fallbacks(case):
 
 
 @pytest.mark.parametrize("pose_chunk", [1, 3, 64])
-def test_pullback_pose_chunking(pose_chunk):
+@pytest.mark.parametrize("algo", [1, 2])
+def test_pullback_pose_chunking(pose_chunk, algo):
     grid = (32, 32)
     d = make_inputs(77, 3, 2, 5000, 11, grid, np.float64)
     _, pb_ref = _oracle_pair(d, grid, np.float64)
-    with forced(pose_chunk=pose_chunk):
+    with forced(pose_chunk=pose_chunk, pullback_algo=algo):
         pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"]), *dev_args(d, np.float64))
+        assert dpr_b200.last_path(1) == ("gather_global" if algo == 1 else "gather2d")
     for k in FIELDS:
         assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-10, k
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n_in", [2, 3])
+@pytest.mark.parametrize("weights", [True, False])
+def test_pullback_paths_agree(dtype, n_in, weights):
+    """generic gather kernel and the 2-d kernel (packed stencil, predicated corner loads, butterfly reduction)."""
+    grid = (40, 24)
+    d = make_inputs(91, n_in, 2, 7001, 13, grid, dtype, weights)
+    # a few far-away / non-finite-free boundary points
+    d["points"][:, :3] = np.array([[5.0, -7.0, 1e30], [0.99, -1.0, 1.0]] + ([[0.0, 0.0, 0.0]] if n_in == 3 else []), dtype=dtype)
+    _, pb_ref = _oracle_pair(d, grid, dtype)
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    for algo in (1, 2):
+        with forced(pullback_algo=algo):
+            pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], td), *dev_args(d, dtype))
+        for k in FIELDS:
+            assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (algo, k)
 
 
 def test_batched_equals_singles():
