@@ -317,10 +317,14 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
             a.d_translation, a.d_out_weight, a.d_point_weight, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
         return DPR_OK;
     };
-    rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true>) : launch(pullback_gather2d_kernel<T, N_IN, K, false>);
+    // paired 8-byte loads need 8-byte aligned rows
+    const bool pair = sizeof(T) == 4 && (a.grid[0] % 2) == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 8) == 0 &&
+                      tuning().pullback_algo != 3;
+    if (pair) rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true, true>) : launch(pullback_gather2d_kernel<T, N_IN, K, false, true>);
+    else rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true, false>) : launch(pullback_gather2d_kernel<T, N_IN, K, false, false>);
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, "gather2d");
+    set_last_path(DPR_OP_PULLBACK, pair ? "gather2d_pair" : "gather2d");
     return DPR_OK;
 }
 

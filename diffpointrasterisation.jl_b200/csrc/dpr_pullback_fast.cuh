@@ -78,7 +78,7 @@ __device__ __forceinline__ void stencil2(const T (&x)[N_IN], const T (&R)[2][N_I
     iy = to_int_sat(ry) - 1;
 }
 
-template <typename T, int N_IN, int K, bool HAS_PW>
+template <typename T, int N_IN, int K, bool HAS_PW, bool PAIR>
 __global__ void __launch_bounds__(256)
 pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ points, const T* __restrict__ rotation,
                          const T* __restrict__ translation, const T* __restrict__ out_weight,
@@ -161,10 +161,33 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
             const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
             const T* base = img + ((int64_t)iy * g[0] + ix);
             T G00 = T(0), G10 = T(0), G01 = T(0), G11 = T(0);
-            if (x_lo && y_lo) G00 = __ldg(base);
-            if (x_hi && y_lo) G10 = __ldg(base + 1);
-            if (x_lo && y_hi) G01 = __ldg(base + g[0]);
-            if (x_hi && y_hi) G11 = __ldg(base + g[0] + 1);
+            if constexpr (std::is_same<T, float>::value && PAIR) {
+                // The L1 cost of a gather is per lane and instruction, and (ix, ix+1) share a 32-byte sector 7 times
+                // out of 8: fetch the 8-byte aligned pair that holds ix with one LDG.64 and only the lanes with odd
+                // ix issue a second 4-byte load (rows are 8-byte aligned: g0 even, checked by the host).
+                const bool odd = ix & 1;
+                const bool both = x_lo && x_hi;
+                const float* pb = base - (odd ? 1 : 0);
+                float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
+                float e0 = 0.f, e1 = 0.f;
+                if (both && y_lo) q0 = __ldg(reinterpret_cast<const float2*>(pb));
+                if (both && y_hi) q1 = __ldg(reinterpret_cast<const float2*>(pb + g[0]));
+                if (both && odd && y_lo) e0 = __ldg(base + 1);
+                if (both && odd && y_hi) e1 = __ldg(base + g[0] + 1);
+                G00 = odd ? q0.y : q0.x; G10 = odd ? e0 : q0.y;
+                G01 = odd ? q1.y : q1.x; G11 = odd ? e1 : q1.y;
+                if (!both) {   // left / right image edge: one column only
+                    if (x_lo && y_lo) G00 = __ldg(base);
+                    if (x_hi && y_lo) G10 = __ldg(base + 1);
+                    if (x_lo && y_hi) G01 = __ldg(base + g[0]);
+                    if (x_hi && y_hi) G11 = __ldg(base + g[0] + 1);
+                }
+            } else {
+                if (x_lo && y_lo) G00 = __ldg(base);
+                if (x_hi && y_lo) G10 = __ldg(base + 1);
+                if (x_lo && y_hi) G01 = __ldg(base + g[0]);
+                if (x_hi && y_hi) G11 = __ldg(base + g[0] + 1);
+            }
             const T du0 = T(1) - dl[0], du1 = T(1) - dl[1];
             // s = sum_c W_c G_c; gx, gy = d/dcoord (differences first: no cancellation against the oracle's f64 sums)
             const T s = du1 * (du0 * G00 + dl[0] * G10) + dl[1] * (du0 * G01 + dl[0] * G11);
