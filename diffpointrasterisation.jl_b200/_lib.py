@@ -23,7 +23,7 @@ SYMBOLS = [
     "dpr_profile_enable", "dpr_profile_count", "dpr_profile_get",
 ]
 
-OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM = range(6)
+OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM, OPT_POINT_SORT = range(7)
 OP_FORWARD, OP_PULLBACK = 0, 1
 
 _lib = None

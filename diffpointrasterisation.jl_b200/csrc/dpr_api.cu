@@ -132,7 +132,7 @@ static int pullback_entry(int n_in, int n_out, const int64_t* grid, int64_t P, i
     DeviceInfo dev;
     rc = current_device_info(dev);
     if (rc != DPR_OK) return rc;
-    if (workspace_bytes < pullback_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
+    if (workspace_bytes < 256) return DPR_ERR_WORKSPACE;   // smaller than dpr_workspace_bytes(): the point sort is skipped
     PullbackArgs<T> a;
     a.n_in = n_in; a.n_out = n_out;
     for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
@@ -293,6 +293,14 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
         size_t have = 0;
         for (int i = 0; i < NSTREAM; ++i) { have = ar->slot_bytes; rc = arena_reserve(ar->slot[i], have, need); if (rc != DPR_OK) return rc; }
         ar->slot_bytes = have;
+    }
+    {   // per-stream kernel workspace (holds the spatially sorted copy of the points)
+        const size_t need_ws = pullback_workspace_bytes(n_in, n_out, grid, P, cb, (int)sizeof(T));
+        if (need_ws > ar->ws_bytes) {
+            size_t have = 0;
+            for (int i = 0; i < NSTREAM; ++i) { have = ar->ws_bytes; rc = arena_reserve(ar->ws[i], have, need_ws); if (rc != DPR_OK) return rc; }
+            ar->ws_bytes = have;
+        }
     }
     char* sh = static_cast<char*>(ar->shared);
     T* d_points = reinterpret_cast<T*>(sh);
@@ -468,6 +476,10 @@ int dpr_host_release(void) {
     if (a.device != dev) return DPR_OK;
     for (int i = 0; i < NSTREAM; ++i) { if (a.slot[i]) cudaFree(a.slot[i]); a.slot[i] = nullptr; }
     a.slot_bytes = 0;
+    for (int i = 0; i < NSTREAM; ++i) { if (a.ws[i]) cudaFree(a.ws[i]); a.ws[i] = nullptr; }
+    a.ws_bytes = 0;
+    for (int i = 0; i < NSTREAM; ++i) { if (cudaMalloc(&a.ws[i], 4096) != cudaSuccess) return DPR_ERR_CUDA; }
+    a.ws_bytes = 4096;
     if (a.shared) cudaFree(a.shared);
     a.shared = nullptr; a.shared_bytes = 0;
     return DPR_OK;
@@ -482,6 +494,7 @@ int dpr_set_option(int option, int64_t value) {
         case DPR_OPT_POINT_SPLIT: g_tuning.point_split = value; return DPR_OK;
         case DPR_OPT_POSE_CHUNK: g_tuning.pose_chunk = value; return DPR_OK;
         case DPR_OPT_FORWARD_ACCUM: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.forward_accum = value; return DPR_OK;
+        case DPR_OPT_POINT_SORT: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.point_sort = value; return DPR_OK;
         default: return DPR_ERR_BAD_OPTION;
     }
 }
@@ -493,6 +506,7 @@ int64_t dpr_get_option(int option) {
         case DPR_OPT_POINT_SPLIT: return g_tuning.point_split;
         case DPR_OPT_POSE_CHUNK: return g_tuning.pose_chunk;
         case DPR_OPT_FORWARD_ACCUM: return g_tuning.forward_accum;
+        case DPR_OPT_POINT_SORT: return g_tuning.point_sort;
         default: return -1;
     }
 }

@@ -21,6 +21,7 @@ struct Tuning {
     int64_t tile_smem_bytes = 0;
     int64_t point_split = 0;
     int64_t pose_chunk = 0;
+    int64_t point_sort = 0;      // pullback: 0 auto, 1 always sort points spatially, 2 never
     int64_t forward_accum = 0;   // 0 auto (fixed point where eligible), 1 float CAS only
 };
 

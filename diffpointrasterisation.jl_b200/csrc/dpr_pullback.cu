@@ -13,6 +13,7 @@
 // which keeps the ds_dout images they gather from resident in L1/L2.
 #include "dpr_common.cuh"
 #include "dpr_internal.h"
+#include "dpr_sort.cuh"
 
 namespace dpr {
 
@@ -63,8 +64,9 @@ pullback_gather_global_kernel(const T* __restrict__ ds_dout, const T* __restrict
                               const T* __restrict__ rotation, const T* __restrict__ translation,
                               const T* __restrict__ out_weight, const T* __restrict__ point_weight,
                               T* __restrict__ d_points, T* __restrict__ d_rotation, T* __restrict__ d_translation,
-                              T* __restrict__ d_out_weight, T* __restrict__ d_point_weight, Grid<T, N_OUT> grid,
-                              int64_t P, int64_t B, int point_chunks, int pose_chunk) {
+                              T* __restrict__ d_out_weight, T* __restrict__ d_point_weight,
+                              const int32_t* __restrict__ perm, Grid<T, N_OUT> grid, int64_t P, int64_t B,
+                              int point_chunks, int pose_chunk) {
     constexpr int NV = PoseGradLayout<N_IN, N_OUT>::NV;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* pose_acc = reinterpret_cast<T*>(smem_raw);  // [pose_chunk][NV]
@@ -136,7 +138,8 @@ pullback_gather_global_kernel(const T* __restrict__ ds_dout, const T* __restrict
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if (!valid[k]) continue;
-        const int64_t p = ((int64_t)pc * K + k) * blockDim.x + threadIdx.x;
+        int64_t p = ((int64_t)pc * K + k) * blockDim.x + threadIdx.x;
+        if (perm) p = __ldg(perm + p);
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) red_add(d_points + p * N_IN + j, dpt[k][j]);
         if (d_point_weight) red_add(d_point_weight + p, dpw[k]);
@@ -213,6 +216,18 @@ static int launch_background_sum(const PullbackArgs<T>& a, int64_t cells, const 
     return DPR_OK;
 }
 
+// Spatial sort of the points pays off once the sort (three small kernels) is amortised over enough poses and there
+// are enough points for a warp's 32 points to be neighbours; it needs the workspace of dpr_workspace_bytes().
+template <typename T>
+static bool use_sort(const PullbackArgs<T>& a) {
+    if (tuning().point_sort == 2) return false;
+    if (a.P >= (int64_t)0x7fffffff) return false;
+    const SortPlan sp = make_sort_plan(a.n_in, a.P, (int)sizeof(T), a.point_weight != nullptr, 256);
+    if (!a.workspace || a.workspace_bytes < sp.total) return false;
+    if (tuning().point_sort == 1) return true;
+    return a.P >= 4096 && a.B >= 4;
+}
+
 template <typename T, int N_IN, int N_OUT>
 static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     constexpr int NV = PoseGradLayout<N_IN, N_OUT>::NV;
@@ -233,6 +248,18 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     int rc = launch_background_sum(a, grid.cells, dev);
     if (rc != DPR_OK) return rc;
     if (a.P == 0 || a.B == 0) return DPR_OK;
+    const T* pts = a.points;
+    const T* pwt = a.point_weight;
+    const int32_t* perm = nullptr;
+    if (use_sort(a)) {
+        const SortPlan sp = make_sort_plan(N_IN, a.P, (int)sizeof(T), a.point_weight != nullptr, 256);
+        rc = sort_points<T, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+        if (rc != DPR_OK) return rc;
+        char* ws = static_cast<char*>(a.workspace);
+        pts = reinterpret_cast<const T*>(ws + sp.off_points);
+        if (a.point_weight) pwt = reinterpret_cast<const T*>(ws + sp.off_pw);
+        perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
+    }
 
     const int threads = 256;
     const int64_t point_chunks = (a.P + (int64_t)threads * K - 1) / ((int64_t)threads * K);
@@ -254,11 +281,11 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     {
         LaunchScope scope("pullback_gather_global", a.stream);
         pullback_gather_global_kernel<T, N_IN, N_OUT, K><<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
-            a.ds_dout, a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.d_points, a.d_rotation,
-            a.d_translation, a.d_out_weight, a.d_point_weight, grid, a.P, a.B, (int)point_chunks, (int)pose_chunk);
+            a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
+            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, a.P, a.B, (int)point_chunks, (int)pose_chunk);
     }
     DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, "gather_global");
+    set_last_path(DPR_OP_PULLBACK, perm ? "gather_global_sorted" : "gather_global");
     return DPR_OK;
 }
 
@@ -294,6 +321,18 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     rc = launch_background_sum(a, grid.cells, dev);
     if (rc != DPR_OK) return rc;
     if (a.P == 0 || a.B == 0) return DPR_OK;
+    const T* pts = a.points;
+    const T* pwt = a.point_weight;
+    const int32_t* perm = nullptr;
+    if (use_sort(a)) {
+        const SortPlan sp = make_sort_plan(N_IN, a.P, (int)sizeof(T), a.point_weight != nullptr, 256);
+        rc = sort_points<T, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+        if (rc != DPR_OK) return rc;
+        char* ws = static_cast<char*>(a.workspace);
+        pts = reinterpret_cast<const T*>(ws + sp.off_points);
+        if (a.point_weight) pwt = reinterpret_cast<const T*>(ws + sp.off_pw);
+        perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
+    }
     const int threads = 256;
     const int64_t point_chunks = (a.P + (int64_t)threads * K - 1) / ((int64_t)threads * K);
     int64_t pose_chunk = tuning().pose_chunk;
@@ -313,8 +352,8 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     auto launch = [&](auto kern) -> int {
         LaunchScope scope("pullback_gather2d", a.stream);
         kern<<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
-            a.ds_dout, a.points, a.rotation, a.translation, a.out_weight, a.point_weight, a.d_points, a.d_rotation,
-            a.d_translation, a.d_out_weight, a.d_point_weight, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
+            a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
+            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
         return DPR_OK;
     };
     // paired 8-byte loads need 8-byte aligned rows
@@ -324,7 +363,7 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     else rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true, false>) : launch(pullback_gather2d_kernel<T, N_IN, K, false, false>);
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, pair ? "gather2d_pair" : "gather2d");
+    set_last_path(DPR_OP_PULLBACK, perm ? (pair ? "gather2d_pair_sorted" : "gather2d_sorted") : (pair ? "gather2d_pair" : "gather2d"));
     return DPR_OK;
 }
 
@@ -343,6 +382,8 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 template int pullback_dispatch<float>(const PullbackArgs<float>&, const DeviceInfo&);
 template int pullback_dispatch<double>(const PullbackArgs<double>&, const DeviceInfo&);
 
-size_t pullback_workspace_bytes(int, int, const int64_t*, int64_t, int64_t, int) { return 0; }
+size_t pullback_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t, int sizeof_T) {
+    return make_sort_plan(n_in, P, sizeof_T, true, 256).total;
+}
 
 }  // namespace dpr

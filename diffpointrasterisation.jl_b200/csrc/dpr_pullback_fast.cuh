@@ -84,7 +84,8 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
                          const T* __restrict__ translation, const T* __restrict__ out_weight,
                          const T* __restrict__ point_weight, T* __restrict__ d_points, T* __restrict__ d_rotation,
                          T* __restrict__ d_translation, T* __restrict__ d_out_weight, T* __restrict__ d_point_weight,
-                         Grid<T, 2> grid, int P, int64_t B, int point_chunks, int pose_chunk) {
+                         const int32_t* __restrict__ perm, Grid<T, 2> grid, int P, int64_t B, int point_chunks,
+                         int pose_chunk) {
     constexpr int NR = 2 * N_IN;            // rotation entries
     constexpr int NV = NR + 3;              // + translation (2) + out_weight
     constexpr int PP = (NV + 3) / 4 * 4;    // padded pose-parameter record: R (col-major), -origin (2), ow
@@ -225,7 +226,8 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         if (!valid[k]) continue;
-        const int p = (pc * K + k) * (int)blockDim.x + (int)threadIdx.x;
+        int p = (pc * K + k) * (int)blockDim.x + (int)threadIdx.x;
+        if (perm) p = __ldg(perm + p);       // points were spatially sorted: write through the permutation
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) red_add(d_points + (int64_t)p * N_IN + j, dpt[k][j]);
         if (d_point_weight) red_add(d_point_weight + p, dpw[k]);

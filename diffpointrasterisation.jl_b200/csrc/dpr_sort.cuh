@@ -1,0 +1,161 @@
+// dpr_sort.cuh - spatial binning of the point cloud (counting sort by Morton code of the point's own coordinates).
+//
+// The pullback gathers ds_dout at the projected position of every point.  With points in their given (arbitrary)
+// order the 32 lanes of a warp hit 32 unrelated 128-byte lines per gather instruction and the L1 data pipe saturates
+// (profiles/: 88 % busy, issue slots 52 %).  A rigid pose maps points that are close in space to pixels that are
+// close in the image, for EVERY pose, so sorting the points once per call along a Z-order curve makes the lanes of a
+// warp land in a small blob of each pose image and share cache lines.  The sort is a three-kernel counting sort
+// (histogram, single-CTA scan, scatter); the order inside a bin is arbitrary.  Gradients are written back through
+// the permutation, so callers never see the reordering.
+#pragma once
+#include "dpr_common.cuh"
+#include "dpr_internal.h"
+
+namespace dpr {
+
+__device__ __forceinline__ uint32_t part1by1(uint32_t x) {   // spread the low 16 bits to even positions
+    x &= 0x0000ffffu;
+    x = (x | (x << 8)) & 0x00ff00ffu;
+    x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u;
+    x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+__device__ __forceinline__ uint32_t part1by2(uint32_t x) {   // spread the low 10 bits to every third position
+    x &= 0x000003ffu;
+    x = (x | (x << 16)) & 0x030000ffu;
+    x = (x | (x << 8)) & 0x0300f00fu;
+    x = (x | (x << 4)) & 0x030c30c3u;
+    x = (x | (x << 2)) & 0x09249249u;
+    return x;
+}
+
+template <typename T, int N_IN>
+__device__ __forceinline__ uint32_t morton_key(const T* __restrict__ points, int64_t p, int bits) {
+    uint32_t q[N_IN];
+    const float cells = (float)(1 << bits);
+#pragma unroll
+    for (int j = 0; j < N_IN; ++j) {
+        // nominal cube is (-1, 1); keep a margin and clamp (NaN -> 0)
+        float c = ((float)__ldg(points + p * N_IN + j) + 1.25f) * (cells / 2.5f);
+        c = fminf(fmaxf(c, 0.f), cells - 1.f);
+        q[j] = (uint32_t)c;
+    }
+    if (N_IN == 2) return part1by1(q[0]) | (part1by1(q[1]) << 1);
+    return part1by2(q[0]) | (part1by2(q[1]) << 1) | (part1by2(q[2]) << 2);
+}
+
+template <typename T, int N_IN>
+__global__ void __launch_bounds__(256) bin_count_kernel(const T* __restrict__ points, int64_t P, int bits,
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ counts) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
+        const uint32_t k = morton_key<T, N_IN>(points, p, bits);
+        keys[p] = k;
+        atomicAdd(counts + k, 1u);
+    }
+}
+
+// exclusive scan of n_bins counters in place (single CTA of 1024 threads; every thread owns a contiguous run)
+__global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t* __restrict__ counts, int n_bins) {
+    __shared__ uint32_t warp_tot[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (n_bins + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = (lo + per < n_bins) ? lo + per : n_bins;
+    uint32_t sum = 0;
+    for (int i = lo; i < hi; ++i) sum += counts[i];
+    uint32_t incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += t;
+        }
+        warp_tot[lane] = w;   // inclusive over warps
+    }
+    __syncthreads();
+    uint32_t run = (warp ? warp_tot[warp - 1] : 0u) + incl - sum;
+    for (int i = lo; i < hi; ++i) {
+        const uint32_t v = counts[i];
+        counts[i] = run;
+        run += v;
+    }
+}
+
+template <typename T, int N_IN>
+__global__ void __launch_bounds__(256) bin_scatter_kernel(const T* __restrict__ points, const T* __restrict__ point_weight,
+                                                          int64_t P, const uint32_t* __restrict__ keys,
+                                                          uint32_t* __restrict__ offsets, int32_t* __restrict__ perm,
+                                                          T* __restrict__ sorted_points, T* __restrict__ sorted_pw) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
+        const uint32_t pos = atomicAdd(offsets + keys[p], 1u);
+        perm[pos] = (int32_t)p;
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) sorted_points[(int64_t)pos * N_IN + j] = __ldg(points + p * N_IN + j);
+        if (point_weight) sorted_pw[pos] = __ldg(point_weight + p);
+    }
+}
+
+struct SortPlan {
+    int bits = 0;             // bits per dimension
+    int n_bins = 0;
+    size_t off_keys = 0, off_counts = 0, off_perm = 0, off_points = 0, off_pw = 0, total = 0;
+};
+
+inline SortPlan make_sort_plan(int n_in, int64_t P, int sizeof_T, bool has_pw, size_t base_offset) {
+    SortPlan sp;
+    int total_bits = 1;
+    while (total_bits < 18 && ((int64_t)1 << total_bits) < 2 * P) ++total_bits;
+    sp.bits = total_bits / n_in;
+    if (sp.bits < 1) sp.bits = 1;
+    if (sp.bits > 9) sp.bits = 9;
+    sp.n_bins = 1 << (sp.bits * n_in);
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    size_t o = al(base_offset);
+    sp.off_keys = o;   o = al(o + sizeof(uint32_t) * (size_t)P);
+    sp.off_counts = o; o = al(o + sizeof(uint32_t) * (size_t)sp.n_bins);
+    sp.off_perm = o;   o = al(o + sizeof(int32_t) * (size_t)P);
+    sp.off_points = o; o = al(o + (size_t)sizeof_T * (size_t)P * n_in);
+    sp.off_pw = o;     o = al(o + (has_pw ? (size_t)sizeof_T * (size_t)P : 0));
+    sp.total = o;
+    return sp;
+}
+
+template <typename T, int N_IN>
+static int sort_points(const T* points, const T* point_weight, int64_t P, void* workspace, const SortPlan& sp,
+                       const DeviceInfo& dev, cudaStream_t stream) {
+    char* ws = static_cast<char*>(workspace);
+    uint32_t* keys = reinterpret_cast<uint32_t*>(ws + sp.off_keys);
+    uint32_t* counts = reinterpret_cast<uint32_t*>(ws + sp.off_counts);
+    int32_t* perm = reinterpret_cast<int32_t*>(ws + sp.off_perm);
+    T* spts = reinterpret_cast<T*>(ws + sp.off_points);
+    T* spw = reinterpret_cast<T*>(ws + sp.off_pw);
+    DPR_CUDA_TRY(cudaMemsetAsync(counts, 0, sizeof(uint32_t) * (size_t)sp.n_bins, stream));
+    int64_t blocks = (P + 255) / 256;
+    if (blocks > (int64_t)dev.sm_count * 16) blocks = (int64_t)dev.sm_count * 16;
+    {
+        LaunchScope scope("bin_count", stream);
+        bin_count_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(points, P, sp.bits, keys, counts);
+    }
+    {
+        LaunchScope scope("bin_scan", stream);
+        bin_scan_kernel<<<1, 1024, 0, stream>>>(counts, sp.n_bins);
+    }
+    {
+        LaunchScope scope("bin_scatter", stream);
+        bin_scatter_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(points, point_weight, P, keys, counts, perm, spts, spw);
+    }
+    DPR_CUDA_TRY(cudaGetLastError());
+    return DPR_OK;
+}
+
+}  // namespace dpr

@@ -118,7 +118,8 @@ enum dpr_option {
     DPR_OPT_TILE_SMEM_BYTES = 2,/* shared-memory budget per CTA for tiles (0 = default)                       */
     DPR_OPT_POINT_SPLIT = 3,    /* forward: force the number of point splits per (pose, slab) (0 = auto)      */
     DPR_OPT_POSE_CHUNK = 4,     /* pullback: force poses per CTA (0 = auto)                                   */
-    DPR_OPT_FORWARD_ACCUM = 5   /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
+    DPR_OPT_FORWARD_ACCUM = 5,  /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
+    DPR_OPT_POINT_SORT = 6      /* pullback: 0 auto, 1 always sort the points spatially first, 2 never        */
 };
 int dpr_set_option(int option, int64_t value);
 int64_t dpr_get_option(int option);

@@ -49,7 +49,7 @@ def test_fast_forward_kernel_has_no_packed_fma():
         assert "FFMA2" not in body
         assert "FMUL2" in body and "ATOMS.ADD" in body
     pb = [c for c in chunks if "pullback_gather2d_kernelIf" in c.split("\n", 1)[0]]
-    assert len(pb) == 4
+    assert len(pb) == 8   # N_in in {2,3} x point weights x paired loads
     for body in pb:
         assert "FFMA2" not in body and "FMUL2" in body
 
