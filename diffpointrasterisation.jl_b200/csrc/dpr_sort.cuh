@@ -63,7 +63,14 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t* __restrict__ c
     const int per = (n_bins + 1023) / 1024;
     const int lo = threadIdx.x * per, hi = (lo + per < n_bins) ? lo + per : n_bins;
     uint32_t sum = 0;
-    for (int i = lo; i < hi; ++i) sum += counts[i];
+    const bool vec = (per & 3) == 0 && hi - lo == per;     // whole 16-byte aligned run
+    if (vec) {
+        const uint4* v4 = reinterpret_cast<const uint4*>(counts + lo);
+#pragma unroll 8
+        for (int i = 0; i < per / 4; ++i) { const uint4 q = v4[i]; sum += q.x + q.y + q.z + q.w; }
+    } else {
+        for (int i = lo; i < hi; ++i) sum += counts[i];
+    }
     uint32_t incl = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -83,10 +90,22 @@ __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t* __restrict__ c
     }
     __syncthreads();
     uint32_t run = (warp ? warp_tot[warp - 1] : 0u) + incl - sum;
-    for (int i = lo; i < hi; ++i) {
-        const uint32_t v = counts[i];
-        counts[i] = run;
-        run += v;
+    if (vec) {
+        uint4* v4 = reinterpret_cast<uint4*>(counts + lo);
+#pragma unroll 4
+        for (int i = 0; i < per / 4; ++i) {
+            const uint4 q = v4[i];
+            uint4 o;
+            o.x = run; o.y = o.x + q.x; o.z = o.y + q.y; o.w = o.z + q.z;
+            run = o.w + q.w;
+            v4[i] = o;
+        }
+    } else {
+        for (int i = lo; i < hi; ++i) {
+            const uint32_t v = counts[i];
+            counts[i] = run;
+            run += v;
+        }
     }
 }
 
@@ -113,8 +132,9 @@ struct SortPlan {
 
 inline SortPlan make_sort_plan(int n_in, int64_t P, int sizeof_T, bool has_pw, size_t base_offset) {
     SortPlan sp;
-    int total_bits = 1;
-    while (total_bits < 18 && ((int64_t)1 << total_bits) < 2 * P) ++total_bits;
+    // ~4 points per bin on average: finer bins do not make a warp's 32 points any more compact
+    int total_bits = 6;
+    while (total_bits < 18 && ((int64_t)4 << total_bits) < P) ++total_bits;
     sp.bits = total_bits / n_in;
     if (sp.bits < 1) sp.bits = 1;
     if (sp.bits > 9) sp.bits = 9;
