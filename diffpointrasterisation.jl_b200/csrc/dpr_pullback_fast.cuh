@@ -117,6 +117,10 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
         valid[k] = p < P;
         const int pp = valid[k] ? p : 0;
         load_point(x[k], points, (int64_t)pp);
+        if (!valid[k]) {   // padding lanes: a far-away point has no in-bounds corner, so the loop needs no extra predicate
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) x[k][j] = T(1e30);
+        }
         pw[k] = HAS_PW ? __ldg(point_weight + pp) : T(1);
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) dpt[k][j] = T(0);
@@ -147,7 +151,10 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
         for (int j = 0; j < N_IN; ++j) { R[0][j] = par[2 * j]; R[1][j] = par[2 * j + 1]; }
         const T neg_origin[2] = {par[NR], par[NR + 1]};
         const T ow = par[NR + 2];
-        const T* __restrict__ img = ds_dout + (b0 + bl) * grid.cells;
+        const T* img = ds_dout + (b0 + bl) * grid.cells;
+        // keep the pose image base as ONE opaque 64-bit register pair: otherwise the compiler re-derives
+        // b*cells + offset with a 64-bit multiply-add and two LEAs for every corner load
+        asm volatile("" : "+l"(img));
 
         T acc[8], acc_ow = T(0);    // acc: d_rotation (col-major, NR values), d_translation (2) [, padding]
 #pragma unroll
@@ -158,9 +165,9 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
             T dl[2];
             stencil2<T, N_IN>(x[k], R, neg_origin, scale, g, ix, iy, dl);
             // per-corner bounds rule (src/raster_pullback.jl:51) as four load predicates
-            const bool x_lo = valid[k] && (unsigned)ix < (unsigned)g[0], x_hi = valid[k] && (unsigned)(ix + 1) < (unsigned)g[0];
+            const bool x_lo = (unsigned)ix < (unsigned)g[0], x_hi = (unsigned)(ix + 1) < (unsigned)g[0];
             const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
-            const T* base = img + ((int64_t)iy * g[0] + ix);
+            const int off = iy * g[0] + ix;          // 32-bit: the host guarantees g0*g1 < 2^30; OOB lanes never load
             T G00 = T(0), G10 = T(0), G01 = T(0), G11 = T(0);
             if constexpr (std::is_same<T, float>::value && PAIR) {
                 // The L1 cost of a gather is per lane and instruction, and (ix, ix+1) share a 32-byte sector 7 times
@@ -168,22 +175,25 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
                 // ix issue a second 4-byte load (rows are 8-byte aligned: g0 even, checked by the host).
                 const bool odd = ix & 1;
                 const bool both = x_lo && x_hi;
-                const float* pb = base - (odd ? 1 : 0);
+                const float* pa = img + (off & ~1);          // one 64-bit address; everything else is an immediate/row offset
+                const float* pr = pa + g[0];
                 float2 q0 = make_float2(0.f, 0.f), q1 = make_float2(0.f, 0.f);
                 float e0 = 0.f, e1 = 0.f;
-                if (both && y_lo) q0 = __ldg(reinterpret_cast<const float2*>(pb));
-                if (both && y_hi) q1 = __ldg(reinterpret_cast<const float2*>(pb + g[0]));
-                if (both && odd && y_lo) e0 = __ldg(base + 1);
-                if (both && odd && y_hi) e1 = __ldg(base + g[0] + 1);
+                if (both && y_lo) q0 = __ldg(reinterpret_cast<const float2*>(pa));
+                if (both && y_hi) q1 = __ldg(reinterpret_cast<const float2*>(pr));
+                if (both && odd && y_lo) e0 = __ldg(pa + 2);
+                if (both && odd && y_hi) e1 = __ldg(pr + 2);
                 G00 = odd ? q0.y : q0.x; G10 = odd ? e0 : q0.y;
                 G01 = odd ? q1.y : q1.x; G11 = odd ? e1 : q1.y;
-                if (!both) {   // left / right image edge: one column only
+                if (!both && (x_lo || x_hi)) {   // left / right image edge: one column only (rare)
+                    const float* base = img + off;
                     if (x_lo && y_lo) G00 = __ldg(base);
                     if (x_hi && y_lo) G10 = __ldg(base + 1);
                     if (x_lo && y_hi) G01 = __ldg(base + g[0]);
                     if (x_hi && y_hi) G11 = __ldg(base + g[0] + 1);
                 }
             } else {
+                const T* base = img + off;
                 if (x_lo && y_lo) G00 = __ldg(base);
                 if (x_hi && y_lo) G10 = __ldg(base + 1);
                 if (x_lo && y_hi) G01 = __ldg(base + g[0]);
