@@ -106,7 +106,7 @@ static int forward_entry(int n_in, int n_out, const int64_t* grid, int64_t P, in
     DeviceInfo dev;
     rc = current_device_info(dev);
     if (rc != DPR_OK) return rc;
-    if (!workspace || workspace_bytes < forward_workspace_bytes(n_in, n_out, grid, P, B, (int)sizeof(T))) return DPR_ERR_WORKSPACE;
+    if (!workspace || workspace_bytes < 256) return DPR_ERR_WORKSPACE;   // smaller than dpr_workspace_bytes(): no point sort
     ForwardArgs<T> a;
     a.n_in = n_in; a.n_out = n_out;
     for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;

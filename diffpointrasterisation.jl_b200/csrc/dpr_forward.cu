@@ -13,6 +13,7 @@
 //                       8-byte aligned; the pose image stays L2-resident because CTAs are ordered pose-major.
 #include "dpr_common.cuh"
 #include "dpr_internal.h"
+#include "dpr_sort.cuh"
 
 namespace dpr {
 
@@ -448,7 +449,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     }
     FastTileParams fp;
     fp.slabs = tp.slabs; fp.splits = tp.splits; fp.rows = tp.rows; fp.band_lo = tp.band_lo; fp.band_hi = tp.band_hi;
-    fp.exclusive = tp.exclusive; fp.fixed_bits = tp.fixed_bits; fp.pw_stats = nullptr;
+    fp.exclusive = tp.exclusive; fp.fixed_bits = tp.fixed_bits; fp.pw_stats = nullptr; fp.aabb = nullptr;
     const int64_t per_split = ((a.P + tp.splits - 1) / tp.splits + kChunk - 1) / kChunk * kChunk;
     fp.per_split = (int)per_split;
     const bool has_pw = a.point_weight != nullptr;
@@ -457,19 +458,39 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
         point_weight_stats_kernel<<<1, 1024, 0, a.stream>>>(a.point_weight, a.P, static_cast<float*>(a.workspace));
         fp.pw_stats = static_cast<const float*>(a.workspace);
     }
+    // Several slabs per pose: sort the points spatially once and let every slab CTA skip the 1024-point runs whose
+    // bounding box cannot reach its rows (otherwise each of the S slabs would transform all P points).
+    const float* pts = a.points;
+    const float* pwt = a.point_weight;
+    const SortPlan sp = make_sort_plan(N_IN, a.P, 4, has_pw, 256);
+    const int64_t n_runs = (a.P + kChunk - 1) / kChunk;
+    const size_t aabb_bytes = sizeof(float) * 2 * N_IN * (size_t)n_runs;
+    if (tp.slabs >= 2 && tuning().point_sort != 2 && a.workspace && a.workspace_bytes >= sp.total + aabb_bytes && a.B >= 2) {
+        int rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+        if (rc != DPR_OK) return rc;
+        char* ws = static_cast<char*>(a.workspace);
+        pts = reinterpret_cast<const float*>(ws + sp.off_points);
+        if (has_pw) pwt = reinterpret_cast<const float*>(ws + sp.off_pw);
+        float* aabb = reinterpret_cast<float*>(ws + sp.total);
+        {
+            LaunchScope scope("chunk_aabb", a.stream);
+            chunk_aabb_kernel<float, N_IN><<<(unsigned)n_runs, 256, 0, a.stream>>>(pts, a.P, kChunk, aabb);
+        }
+        fp.aabb = aabb;
+    }
     const int64_t ctas = a.B * tp.slabs * tp.splits;
     auto launch = [&](auto kern) -> int {
         DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         LaunchScope scope("fwd_tile2d_fast", a.stream);
-        kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(a.points, a.rotation, a.translation, a.background,
-                                                             a.out_weight, a.point_weight, a.out, grid, (int)a.P, fp);
+        kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(pts, a.rotation, a.translation, a.background,
+                                                             a.out_weight, pwt, a.out, grid, (int)a.P, fp);
         return DPR_OK;
     };
     int rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true>) : launch(fwd_tile2d_fast_kernel<N_IN, false>);
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
     const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];
-    set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid_fixed" : (tp.slabs > 1 ? "tile2d_slabs_fixed" : (tp.exclusive ? "tile2d_fixed" : "tile2d_split_fixed")));
+    set_last_path(DPR_OP_FORWARD, border ? "tile2d_hybrid_fixed" : (tp.slabs > 1 ? (fp.aabb ? "tile2d_slabs_culled_fixed" : "tile2d_slabs_fixed") : (tp.exclusive ? "tile2d_fixed" : "tile2d_split_fixed")));
     return DPR_OK;
 }
 
@@ -498,6 +519,10 @@ int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
 template int forward_dispatch<float>(const ForwardArgs<float>&, const DeviceInfo&);
 template int forward_dispatch<double>(const ForwardArgs<double>&, const DeviceInfo&);
 
-size_t forward_workspace_bytes(int, int, const int64_t*, int64_t, int64_t, int) { return 256; }
+size_t forward_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t, int sizeof_T) {
+    // point-weight statistics (256 B) + room for the spatially sorted copy of the points and their run boxes
+    const SortPlan sp = make_sort_plan(n_in, P, sizeof_T, true, 256);
+    return sp.total + sizeof(float) * 2 * (size_t)n_in * (size_t)((P + 1023) / 1024) + 256;
+}
 
 }  // namespace dpr

@@ -54,12 +54,13 @@ struct FastTileParams {
     int fixed_bits;
     int per_split;             // points per split, a multiple of kChunk
     const float* pw_stats;     // {max, min, mean} of point_weight or NULL
+    const float* aabb;         // per-kChunk bounding boxes of the (spatially sorted) points, or NULL: no culling
 };
 
 // shared-memory carve-up (bytes) after the tile
 __host__ __device__ inline size_t fast_extra_smem(int n_in, bool has_pw) {
     (void)n_in; (void)has_pw;
-    return (size_t)32 * kQueueCap * 4;
+    return (size_t)32 * kQueueCap * 4 + (size_t)kChunk * 4;   // per-warp deferred-point queues + surviving-chunk list
 }
 
 template <int N_IN, bool HAS_PW>
@@ -84,6 +85,8 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
     float* tile_f = reinterpret_cast<float*>(smem_raw);
     unsigned char* after = smem_raw + (((size_t)tile_cap * 4 + 127) / 128) * 128;
     int* queue = reinterpret_cast<int*>(after);
+    int* clist = queue + 32 * kQueueCap;             // chunks of the current round that can touch this slab
+    __shared__ int s_count;
     float* __restrict__ img = out + b * grid.cells;
     const float bg = background ? __ldg(background + b) : 0.f;
     const bool border = (tp.band_lo > 0 || tp.band_hi < g1);
@@ -176,24 +179,56 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         };
 
         const int n_chunks = (p_end - p_begin + kChunk - 1) / kChunk;
+        const bool cull = tp.aabb != nullptr;
+        for (int round = 0; round < n_chunks; round += kChunk) {
+        // ---- which chunks of this round can touch the slab?  (spatially sorted points + per-chunk boxes) ----------
+        int n_iter = (n_chunks - round < kChunk) ? n_chunks - round : kChunk;
+        if (cull) {
+            if (threadIdx.x == 0) s_count = 0;
+            __syncthreads();
+            const int c = round + (int)threadIdx.x;
+            bool keep = false;
+            if (c < n_chunks) {
+                const float* bx = tp.aabb + ((int64_t)(p_begin / kChunk) + c) * 2 * N_IN;
+                float cy = -pose.origin[1], hy = 0.f;
+#pragma unroll
+                for (int j = 0; j < N_IN; ++j) {
+                    cy = fmaf(pose.R[1][j], __ldg(bx + j), cy);
+                    hy = fmaf(fabsf(pose.R[1][j]), __ldg(bx + N_IN + j), hy);
+                }
+                cy *= grid.scale[1];
+                hy = hy * grid.scale[1] + 1.0f + 1e-3f * fabsf(cy);      // conservative: one row + rounding slack
+                // a point at row coordinate y touches rows [y - 1.5, y + 0.5]
+                keep = !(cy + hy + 0.5f < (float)ys) && !(cy - hy - 1.5f > (float)(ye - 1));
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, keep);
+            int base = 0;
+            if (lane == 0 && m) base = atomicAdd(&s_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) clist[base + __popc(m & ((1u << lane) - 1u))] = c;
+            __syncthreads();
+            n_iter = s_count;
+        }
+        auto chunk_of = [&](int i) -> int { return cull ? clist[i] : round + i; };
         // software pipeline: the point of the next chunk is loaded while the current one is processed
         float xn[N_IN], pwn = 1.f;
-        {
-            const int p0 = p_begin + (int)threadIdx.x;
+        if (n_iter > 0) {
+            const int p0 = p_begin + chunk_of(0) * kChunk + (int)threadIdx.x;
             if (p0 < p_end) {
                 load_point(xn, points, (int64_t)p0);
                 if (HAS_PW) pwn = __ldg(point_weight + p0);
             }
         }
-        for (int c = 0; c < n_chunks; ++c) {
+        for (int it = 0; it < n_iter; ++it) {
+            const int c = chunk_of(it);
             const int c0 = p_begin + c * kChunk;
             const bool active = c0 + (int)threadIdx.x < p_end;
             float x[N_IN];
 #pragma unroll
             for (int j = 0; j < N_IN; ++j) x[j] = xn[j];
             const float pw = pwn;
-            {
-                const int pn = c0 + kChunk + (int)threadIdx.x;
+            if (it + 1 < n_iter) {
+                const int pn = p_begin + chunk_of(it + 1) * kChunk + (int)threadIdx.x;
                 if (pn < p_end) {
                     load_point(xn, points, (int64_t)pn);
                     if (HAS_PW) pwn = __ldg(point_weight + pn);
@@ -243,7 +278,11 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                     __syncwarp();
                 }
             }
-            if ((c & 63) == 63) { mass += mass32; mass32 = 0; }
+            if ((it & 63) == 63) { mass += mass32; mass32 = 0; }
+        }
+        mass += mass32;
+        mass32 = 0;
+        if (cull) __syncthreads();     // the chunk list is rebuilt in the next round
         }
         if (lane < wq_count) slow_point(wq[lane]);
         mass += mass32;

@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(256) bin_count_kernel(const T* __restrict__ po
 // exclusive scan of n_bins counters in place (single CTA of 1024 threads).  Each WARP owns a contiguous segment and
 // walks it with coalesced 16-byte loads (a per-thread contiguous run made every load touch 32 lines: 117 us for 2^18
 // bins); the 32 segment totals are scanned once in between.
-__global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t* __restrict__ counts, int n_bins) {
+static __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t* __restrict__ counts, int n_bins) {
     __shared__ uint32_t warp_tot[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (n_bins < 4096 || (n_bins & 4095)) {
@@ -146,6 +146,46 @@ __global__ void __launch_bounds__(256) bin_scatter_kernel(const T* __restrict__ 
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) sorted_points[(int64_t)pos * N_IN + j] = __ldg(points + p * N_IN + j);
         if (point_weight) sorted_pw[pos] = __ldg(point_weight + p);
+    }
+}
+
+// Axis-aligned bounding box (centre, half extent) of every run of `chunk` consecutive (sorted) points: lets a CTA
+// skip whole runs that cannot touch its tile.  One CTA of 256 threads per run.
+template <typename T, int N_IN>
+__global__ void __launch_bounds__(256) chunk_aabb_kernel(const T* __restrict__ points, int64_t P, int chunk,
+                                                         float* __restrict__ aabb) {
+    const int64_t lo = (int64_t)blockIdx.x * chunk;
+    const int64_t hi = (lo + chunk < P) ? lo + chunk : P;
+    float mn[N_IN], mx[N_IN];
+#pragma unroll
+    for (int j = 0; j < N_IN; ++j) { mn[j] = 3.4e38f; mx[j] = -3.4e38f; }
+    for (int64_t p = lo + threadIdx.x; p < hi; p += blockDim.x) {
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) {
+            const float v = (float)__ldg(points + p * N_IN + j);
+            mn[j] = fminf(mn[j], v);
+            mx[j] = fmaxf(mx[j], v);
+        }
+    }
+    __shared__ float smn[8][N_IN], smx[8][N_IN];
+#pragma unroll
+    for (int j = 0; j < N_IN; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[j] = fminf(mn[j], __shfl_xor_sync(0xffffffffu, mn[j], o));
+            mx[j] = fmaxf(mx[j], __shfl_xor_sync(0xffffffffu, mx[j], o));
+        }
+        if ((threadIdx.x & 31) == 0) { smn[threadIdx.x >> 5][j] = mn[j]; smx[threadIdx.x >> 5][j] = mx[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < N_IN) {
+        const int j = threadIdx.x;
+        float a = smn[0][j], b = smx[0][j];
+        for (int w = 1; w < 8; ++w) { a = fminf(a, smn[w][j]); b = fmaxf(b, smx[w][j]); }
+        // widen a little: the Float64 points were rounded to float for the box
+        const float ctr = 0.5f * (a + b), half = 0.5f * (b - a) * 1.0001f + 1e-6f * (fabsf(a) + fabsf(b));
+        aabb[(int64_t)blockIdx.x * 2 * N_IN + j] = ctr;
+        aabb[(int64_t)blockIdx.x * 2 * N_IN + N_IN + j] = half;
     }
 }
 

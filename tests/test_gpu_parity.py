@@ -119,6 +119,25 @@ def test_forward_fixed_point_and_float_accumulation_agree(weights):
     assert torch.equal(a1, a2), "integer accumulation must not depend on the order of the atomics"
 
 
+@pytest.mark.parametrize("n_in", [2, 3])
+def test_forward_slabs_with_chunk_culling(n_in):
+    """Several slabs per pose: points are sorted spatially and each slab CTA skips the 1024-point runs whose bounding
+    box cannot reach its rows; the image must not change (dense and sparse clouds, points outside the cube)."""
+    grid = (64, 96)
+    d = make_inputs(555, n_in, 2, 50000, 6, grid, np.float32)
+    d["points"][:, :100] *= 4.0          # some points far outside
+    out_ref, _ = _oracle_pair(d, grid, np.float32)
+    args = dev_args(d, np.float32)
+    with forced(forward_algo=2, tile_smem_bytes=20 * 64 * 4):
+        out = dpr_b200.raster(grid, *args)
+        assert dpr_b200.last_path(0) == "tile2d_slabs_culled_fixed"
+    with forced(forward_algo=2, tile_smem_bytes=20 * 64 * 4, point_sort=2):
+        out2 = dpr_b200.raster(grid, *args)
+        assert dpr_b200.last_path(0) == "tile2d_slabs_fixed"
+    assert rel_l2(to_np(out), out_ref) <= 1e-5 and rel_l2(to_np(out2), out_ref) <= 1e-5
+    assert torch.equal(out, out2), "fixed-point accumulation is order independent: culling must not change a bit"
+
+
 @pytest.mark.parametrize("case", ["wrap", "negative_out_weight", "negative_point_weight", "wide_dynamic_range", "zero_weight"])
 def test_forward_fixed_point_fallbacks(case):
     """Inputs the fixed-point mode must not mishandle: a cell that wraps 32 bits (thousands of coincident points),
