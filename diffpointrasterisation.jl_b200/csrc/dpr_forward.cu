@@ -288,19 +288,19 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
     }
 }
 
-// {max, min, mean} of point_weight, for the fixed-point eligibility test (single CTA; P floats are a few MB at most)
-__global__ void __launch_bounds__(1024) point_weight_stats_kernel(const float* __restrict__ pw, int64_t P, float* __restrict__ stats) {
-    float mx = -3.4e38f, mn = 3.4e38f;
-    double sum = 0.0;
-    for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+// {max, min, mean} of point_weight, for the fixed-point eligibility test: per-CTA partials, then a one-CTA finish
+__global__ void __launch_bounds__(256) point_weight_stats_partial_kernel(const float* __restrict__ pw, int64_t P,
+                                                                         float* __restrict__ partial /* [grid][4] */) {
+    float mx = -3.4e38f, mn = 3.4e38f, sum = 0.f;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
         const float w = __ldg(pw + i);
         mx = fmaxf(mx, w);
         mn = fminf(mn, w);
-        sum += (double)w;
+        sum += w;
         if (!(w == w)) mn = -1.f;    // NaN weights disable the fixed-point mode
     }
-    __shared__ float smx[32], smn[32];
-    __shared__ double ssum[32];
+    __shared__ float smx[8], smn[8], ssum[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -310,9 +310,26 @@ __global__ void __launch_bounds__(1024) point_weight_stats_kernel(const float* _
     if ((threadIdx.x & 31) == 0) { smx[threadIdx.x >> 5] = mx; smn[threadIdx.x >> 5] = mn; ssum[threadIdx.x >> 5] = sum; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int i = 1; i < 32; ++i) { mx = fmaxf(mx, smx[i]); mn = fminf(mn, smn[i]); sum += ssum[i]; }
-        stats[0] = mx; stats[1] = mn; stats[2] = (float)(sum / (double)(P > 0 ? P : 1));
+        for (int i = 1; i < 8; ++i) { mx = fmaxf(mx, smx[i]); mn = fminf(mn, smn[i]); sum += ssum[i]; }
+        partial[blockIdx.x * 4] = mx; partial[blockIdx.x * 4 + 1] = mn; partial[blockIdx.x * 4 + 2] = sum;
     }
+}
+__global__ void __launch_bounds__(32) point_weight_stats_finish_kernel(const float* __restrict__ partial, int n, int64_t P,
+                                                                       float* __restrict__ stats) {
+    float mx = -3.4e38f, mn = 3.4e38f;
+    double sum = 0.0;
+    for (int i = threadIdx.x; i < n; i += 32) {
+        mx = fmaxf(mx, partial[i * 4]);
+        mn = fminf(mn, partial[i * 4 + 1]);
+        sum += (double)partial[i * 4 + 2];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+        sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    }
+    if (threadIdx.x == 0) { stats[0] = mx; stats[1] = mn; stats[2] = (float)(sum / (double)(P > 0 ? P : 1)); }
 }
 
 }  // namespace dpr
@@ -367,7 +384,8 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
     // Float32 with 16-byte aligned inputs takes the TMA-staged fixed-point kernel, which needs staging space
     use_fast = sizeof(T) == 4 && tuning().forward_accum != 1 && (reinterpret_cast<uintptr_t>(a.points) & 15) == 0 &&
                (!a.point_weight || ((reinterpret_cast<uintptr_t>(a.point_weight) & 15) == 0 && a.workspace && a.workspace_bytes >= 16));
-    const int64_t extra = use_fast ? (int64_t)fast_extra_smem(a.n_in, a.point_weight != nullptr) + 128 : 0;
+    int64_t extra = use_fast ? (int64_t)fast_extra_smem(false) + 128 : 0;
+    const int64_t extra_cull = use_fast ? (int64_t)fast_extra_smem(true) - (int64_t)fast_extra_smem(false) : 0;
     if (use_fast && tuning().tile_smem_bytes == 0) budget -= extra;
     const int64_t row_bytes = g0 * (int64_t)sizeof(T);
     const int64_t rows_fit = budget / row_bytes;
@@ -384,10 +402,14 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
         tp.band_lo = (int)((g1 - rows_fit) / 2);
         tp.band_hi = tp.band_lo + (int)rows_fit;
     } else {
-        const int64_t S = (g1 + rows_fit - 1) / rows_fit;
+        // several slabs: leave room for the surviving-chunk list of the culling kernel
+        const int64_t rows_fit2 = (tuning().tile_smem_bytes == 0 ? budget - extra_cull : budget) / row_bytes;
+        if (rows_fit2 < 8) return false;
+        const int64_t S = (g1 + rows_fit2 - 1) / rows_fit2;
         if (S > 8) return false;
         tp.slabs = (int)S;
         tp.rows = (int)((g1 + S - 1) / S);
+        extra += extra_cull;
     }
     // point splits: fill the machine when there are few (pose, slab) pairs
     int64_t Q = 1;
@@ -454,9 +476,20 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     fp.per_split = (int)per_split;
     const bool has_pw = a.point_weight != nullptr;
     if (has_pw) {
-        LaunchScope scope("point_weight_stats", a.stream);
-        point_weight_stats_kernel<<<1, 1024, 0, a.stream>>>(a.point_weight, a.P, static_cast<float*>(a.workspace));
-        fp.pw_stats = static_cast<const float*>(a.workspace);
+        // statistics live in the first 256 bytes of the workspace: [0..3] result, [4..] up to 15 CTA partials
+        float* stats = static_cast<float*>(a.workspace);
+        int n_part = (int)((a.P + 65535) / 65536);
+        if (n_part > 15) n_part = 15;
+        if (n_part < 1) n_part = 1;
+        {
+            LaunchScope scope("point_weight_stats", a.stream);
+            point_weight_stats_partial_kernel<<<n_part, 256, 0, a.stream>>>(a.point_weight, a.P, stats + 4);
+        }
+        {
+            LaunchScope scope("point_weight_stats_finish", a.stream);
+            point_weight_stats_finish_kernel<<<1, 32, 0, a.stream>>>(stats + 4, n_part, a.P, stats);
+        }
+        fp.pw_stats = stats;
     }
     // Several slabs per pose: sort the points spatially once and let every slab CTA skip the 1024-point runs whose
     // bounding box cannot reach its rows (otherwise each of the S slabs would transform all P points).
@@ -486,7 +519,9 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
                                                              a.out_weight, pwt, a.out, grid, (int)a.P, fp);
         return DPR_OK;
     };
-    int rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true>) : launch(fwd_tile2d_fast_kernel<N_IN, false>);
+    int rc;
+    if (fp.aabb) rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, true>) : launch(fwd_tile2d_fast_kernel<N_IN, false, true>);
+    else rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, false>) : launch(fwd_tile2d_fast_kernel<N_IN, false, false>);
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
     const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];

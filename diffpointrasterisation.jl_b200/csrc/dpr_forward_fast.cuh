@@ -22,33 +22,6 @@ namespace dpr {
 constexpr int kChunk = 1024;          // points per TMA chunk = threads per CTA
 constexpr int kQueueCap = 64;         // per-warp deferred-point queue (ints)
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// 1-d bulk copy global -> shared through the TMA unit, completion counted in bytes on `bar`
-__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 struct FastTileParams {
     int slabs, splits, rows, band_lo, band_hi, exclusive;
     int fixed_bits;
@@ -58,12 +31,12 @@ struct FastTileParams {
 };
 
 // shared-memory carve-up (bytes) after the tile
-__host__ __device__ inline size_t fast_extra_smem(int n_in, bool has_pw) {
-    (void)n_in; (void)has_pw;
-    return (size_t)32 * kQueueCap * 4 + (size_t)kChunk * 4;   // per-warp deferred-point queues + surviving-chunk list
+__host__ __device__ inline size_t fast_extra_smem(bool cull) {
+    // per-warp deferred-point queues [+ surviving-chunk list when slab CTAs cull point runs]
+    return (size_t)32 * kQueueCap * 4 + (cull ? (size_t)kChunk * 4 : 0);
 }
 
-template <int N_IN, bool HAS_PW>
+template <int N_IN, bool HAS_PW, bool CULL>
 __global__ void __launch_bounds__(1024, 1)
 fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict__ rotation,
                        const float* __restrict__ translation, const float* __restrict__ background,
@@ -179,11 +152,10 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         };
 
         const int n_chunks = (p_end - p_begin + kChunk - 1) / kChunk;
-        const bool cull = tp.aabb != nullptr;
-        for (int round = 0; round < n_chunks; round += kChunk) {
+        for (int round = 0; round < n_chunks; round += (CULL ? kChunk : n_chunks)) {
         // ---- which chunks of this round can touch the slab?  (spatially sorted points + per-chunk boxes) ----------
-        int n_iter = (n_chunks - round < kChunk) ? n_chunks - round : kChunk;
-        if (cull) {
+        int n_iter = CULL ? ((n_chunks - round < kChunk) ? n_chunks - round : kChunk) : n_chunks;
+        if constexpr (CULL) {
             if (threadIdx.x == 0) s_count = 0;
             __syncthreads();
             const int c = round + (int)threadIdx.x;
@@ -209,7 +181,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
             __syncthreads();
             n_iter = s_count;
         }
-        auto chunk_of = [&](int i) -> int { return cull ? clist[i] : round + i; };
+        auto chunk_of = [&](int i) -> int { if constexpr (CULL) return clist[i]; else return round + i; };
         // software pipeline: the point of the next chunk is loaded while the current one is processed
         float xn[N_IN], pwn = 1.f;
         if (n_iter > 0) {
@@ -282,7 +254,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         }
         mass += mass32;
         mass32 = 0;
-        if (cull) __syncthreads();     // the chunk list is rebuilt in the next round
+        if constexpr (CULL) __syncthreads();     // the chunk list is rebuilt in the next round
         }
         if (lane < wq_count) slow_point(wq[lane]);
         mass += mass32;

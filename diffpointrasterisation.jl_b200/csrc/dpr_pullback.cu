@@ -291,6 +291,7 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 
 }  // namespace dpr
 #include "dpr_pullback_fast.cuh"
+#include "dpr_pullback_tma.cuh"
 namespace dpr {
 
 // zero everything that is accumulated with REDG (ext/DiffPointRasterisationCUDAExt.jl:272-276)
@@ -367,8 +368,87 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     return DPR_OK;
 }
 
+// Float32 images that fit a 2- or 3-stage shared-memory ring: TMA-staged kernel (dpr_pullback_tma.cuh)
+template <int N_IN>
+static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, int stages) {
+    constexpr int K = 8;
+    Grid<float, 2> grid;
+    grid.cells = 1;
+    for (int k = 0; k < 2; ++k) {
+        grid.g[k] = (int)a.grid[k];
+        grid.scale[k] = float(a.grid[k]) / 2.f;
+        grid.cells *= a.grid[k];
+    }
+    int rc = zero_gradients(a);
+    if (rc != DPR_OK) return rc;
+    if (a.P == 0 || a.B == 0) return launch_background_sum(a, grid.cells, dev);
+    const float* pts = a.points;
+    const float* pwt = a.point_weight;
+    const int32_t* perm = nullptr;
+    if (use_sort(a)) {
+        const SortPlan sp = make_sort_plan(N_IN, a.P, 4, a.point_weight != nullptr, 256);
+        rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+        if (rc != DPR_OK) return rc;
+        char* ws = static_cast<char*>(a.workspace);
+        pts = reinterpret_cast<const float*>(ws + sp.off_points);
+        if (a.point_weight) pwt = reinterpret_cast<const float*>(ws + sp.off_pw);
+        perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
+    }
+    const int64_t ppc = (int64_t)kTmaConsumers * K;
+    const int64_t point_chunks = (a.P + ppc - 1) / ppc;
+    // pose chunks: fill whole waves of one CTA per SM, keep chunks long enough to amortise the per-point REDGs
+    int64_t pose_chunks = 1;
+    if (tuning().pose_chunk > 0) {
+        pose_chunks = (a.B + tuning().pose_chunk - 1) / tuning().pose_chunk;
+    } else {
+        double best = 1e30;
+        for (int64_t m = 1; m <= 16 && m <= a.B; ++m) {
+            if (a.B / m < 32 && m > 1) break;
+            const int64_t n = point_chunks * m;
+            const int64_t waves = (n + dev.sm_count - 1) / dev.sm_count;
+            const double cost = (double)waves * dev.sm_count / (double)n + 0.01 * m;   // wave inefficiency + REDG overhead
+            if (cost < best) { best = cost; pose_chunks = m; }
+        }
+    }
+    const int64_t pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
+    pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
+    if (point_chunks * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
+    const size_t smem = tma_pullback_smem(grid.cells, stages, N_IN);
+    const bool has_pw = a.point_weight != nullptr;
+    auto launch = [&](auto kern) -> int {
+        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchScope scope("pullback_tma2d", a.stream);
+        kern<<<(unsigned)(point_chunks * pose_chunks), kTmaConsumers + 32, smem, a.stream>>>(
+            a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation, a.d_translation,
+            a.d_background, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
+        return DPR_OK;
+    };
+    if (stages == 3) rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 3>) : launch(pullback_tma2d_kernel<N_IN, K, false, 3>);
+    else rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 2>) : launch(pullback_tma2d_kernel<N_IN, K, false, 2>);
+    if (rc != DPR_OK) return rc;
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_PULLBACK, perm ? "tma2d_sorted" : "tma2d");
+    return DPR_OK;
+}
+
 template <typename T>
 int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
+    if constexpr (sizeof(T) == 4) {
+        // TMA-staged kernel: whole pose image on chip, 16-byte aligned images, enough points to fill the CTAs
+        const int64_t cells2 = a.n_out == 2 ? a.grid[0] * a.grid[1] : 0;
+        const int64_t algo = tuning().pullback_algo;
+        if (a.n_out == 2 && (algo == 0 || algo == 4) && cells2 > 0 && (cells2 % 4) == 0 &&
+            (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && a.P < (int64_t)0x3fffffff) {
+            int stages = 0;
+            if (tma_pullback_smem(cells2, 3, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 3;
+            else if (tma_pullback_smem(cells2, 2, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 2;
+            const bool worth = algo == 4 || (a.P >= 4 * (int64_t)kTmaConsumers * 8 && a.B >= 16);
+            if (stages && worth) {
+                if (a.n_in == 2) return pullback_tma2d<2>(a, dev, stages);
+                if (a.n_in == 3) return pullback_tma2d<3>(a, dev, stages);
+            }
+        }
+    }
     if (a.n_out == 2 && tuning().pullback_algo != 1 && a.P < (int64_t)0x3fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff) {
         if (a.n_in == 2) return pullback_gather2d<T, 2>(a, dev);
         if (a.n_in == 3) return pullback_gather2d<T, 3>(a, dev);

@@ -1,0 +1,222 @@
+// dpr_pullback_tma.cuh - 2-d Float32 pullback for pose images that fit in shared memory (included by dpr_pullback.cu).
+//
+// When a whole ds_dout pose image is at most ~64 KB (e.g. 128 x 128 Float32, BASELINE config 5) it is cheaper to bring
+// it on chip once per (CTA, pose) than to gather it through L1: a dedicated producer warp streams the images of the
+// CTA's pose chunk into a 3-stage shared-memory ring with the TMA unit (cp.async.bulk, one instruction per 64 KB
+// image, completion counted on an mbarrier), 15 consumer warps gather with LDS (2.6 T gathers/s vs 0.8 T/s through
+// L1, profiles/probe_atomics_r01.json) and release the stage through an "empty" mbarrier.  A thread still OWNS its
+// K points across all poses, so d_points needs one REDG per point and pose chunk.  While the consumers work, the
+// otherwise idle producer warp sums the staged image: d_background comes from the SAME read of ds_dout
+// (ds_dout crosses HBM once), replacing the separate background_sum pass.
+#pragma once
+#include "dpr_common.cuh"
+#include "dpr_pullback_fast.cuh"  // stencil2, butterfly8
+
+namespace dpr {
+
+constexpr int kTmaConsumers = 480;      // consumer threads (15 warps) + 32 producer threads = 512 (128 registers each)
+constexpr int kTmaRound = 64;           // poses whose parameters / accumulators are resident at a time
+
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+
+template <int N_IN, int K, bool HAS_PW, int STAGES>
+__global__ void __launch_bounds__(kTmaConsumers + 32, 1)
+pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict__ points,
+                      const float* __restrict__ rotation, const float* __restrict__ translation,
+                      const float* __restrict__ out_weight, const float* __restrict__ point_weight,
+                      float* __restrict__ d_points, float* __restrict__ d_rotation, float* __restrict__ d_translation,
+                      float* __restrict__ d_background, float* __restrict__ d_out_weight,
+                      float* __restrict__ d_point_weight, const int32_t* __restrict__ perm, Grid<float, 2> grid, int P,
+                      int64_t B, int point_chunks, int pose_chunk) {
+    constexpr int NR = 2 * N_IN, NV = NR + 3, PP = (NV + 3) / 4 * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int cells = (int)grid.cells;
+    const uint32_t img_bytes = (uint32_t)cells * 4u;
+    const size_t stage_stride = ((size_t)img_bytes + 127) / 128 * 128;
+    float* tiles = reinterpret_cast<float*>(smem_raw);
+    unsigned char* after = smem_raw + stage_stride * STAGES;
+    float* pose_par = reinterpret_cast<float*>(after);                 // [kTmaRound][PP]
+    float* pose_acc = pose_par + kTmaRound * PP;                       // [kTmaRound][NV]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pose_acc + kTmaRound * NV + ((kTmaRound * NV) & 1));   // full[S], empty[S]
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+
+    const int pc = blockIdx.x % point_chunks;
+    const int64_t bc = blockIdx.x / point_chunks;
+    const int64_t b0 = bc * pose_chunk;
+    const int n_pose = (int)((b0 + pose_chunk < B ? b0 + pose_chunk : B) - b0);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_producer = warp == kTmaConsumers / 32;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kTmaConsumers / 32 + 1);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (is_producer) {
+        // ===== producer warp: TMA ring + d_background ==========================================================
+        const bool do_bg = d_background != nullptr && pc == 0;
+        auto issue = [&](int i) {      // lane 0 only
+            const int s = i % STAGES;
+            mbar_arrive_expect_tx(&full[s], img_bytes);
+            tma_load_1d(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s, ds_dout + (b0 + i) * (int64_t)cells,
+                        img_bytes, &full[s]);
+        };
+        if (lane == 0)
+            for (int i = 0; i < STAGES - 1 && i < n_pose; ++i) issue(i);
+        for (int i = 0; i < n_pose; ++i) {
+            const int j = i + STAGES - 1;           // keep STAGES-1 images in flight ahead of the consumers
+            if (j < n_pose) {
+                if (j >= STAGES) mbar_wait(&empty[j % STAGES], ((j / STAGES) - 1) & 1);
+                if (lane == 0) issue(j);
+            }
+            const int s = i % STAGES;
+            if (do_bg) {
+                mbar_wait(&full[s], (i / STAGES) & 1);
+                const float4* t4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s);
+                float acc0 = 0.f, acc1 = 0.f;
+                for (int q = lane; q < cells / 4; q += 32) {
+                    const float4 v = t4[q];
+                    acc0 += v.x + v.y;
+                    acc1 += v.z + v.w;
+                }
+                const float tot = warp_sum(acc0 + acc1);
+                if (lane == 0) d_background[b0 + i] = tot;      // src/raster_pullback.jl:78
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+        return;
+    }
+
+    // ===== consumer warps ======================================================================================
+    float x[K][N_IN], pw[K], dpt[K][N_IN], dpw[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = (pc * K + k) * kTmaConsumers + (int)threadIdx.x;
+        const bool valid = p < P;
+        const int pp = valid ? p : 0;
+        load_point(x[k], points, (int64_t)pp);
+        pw[k] = HAS_PW ? __ldg(point_weight + pp) : 1.f;
+        if (!valid) {
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) x[k][j] = 1e30f;      // padding lanes: no in-bounds corner
+        }
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) dpt[k][j] = 0.f;
+        dpw[k] = 0.f;
+    }
+    const int g[2] = {grid.g[0], grid.g[1]};
+    const float scale[2] = {grid.scale[0], grid.scale[1]};
+    const int vsel = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+
+    for (int r0 = 0; r0 < n_pose; r0 += kTmaRound) {
+        const int n_round = (n_pose - r0 < kTmaRound) ? n_pose - r0 : kTmaRound;
+        // stage this round's pose parameters, clear its accumulators (consumer warps only: named barrier 1)
+        for (int i = threadIdx.x; i < n_round * PP; i += kTmaConsumers) {
+            const int bl = i / PP, v = i % PP;
+            const int64_t b = b0 + r0 + bl;
+            float val = 0.f;
+            if (v < NR) val = __ldg(rotation + b * NR + v);
+            else if (v < NR + 2) val = -sub_rn(-1.f, __ldg(translation + b * 2 + (v - NR)));
+            else if (v == NR + 2) val = out_weight ? __ldg(out_weight + b) : 1.f;
+            pose_par[i] = val;
+        }
+        for (int i = threadIdx.x; i < n_round * NV; i += kTmaConsumers) pose_acc[i] = 0.f;
+        named_bar_sync(1, kTmaConsumers);
+
+        for (int bl = 0; bl < n_round; ++bl) {
+            const int i = r0 + bl;
+            const int s = i % STAGES;
+            float par[PP];
+#pragma unroll
+            for (int q = 0; q < PP / 4; ++q) {
+                const float4 v = reinterpret_cast<const float4*>(pose_par + bl * PP)[q];
+                par[4 * q] = v.x; par[4 * q + 1] = v.y; par[4 * q + 2] = v.z; par[4 * q + 3] = v.w;
+            }
+            float R[2][N_IN];
+#pragma unroll
+            for (int j = 0; j < N_IN; ++j) { R[0][j] = par[2 * j]; R[1][j] = par[2 * j + 1]; }
+            const float neg_origin[2] = {par[NR], par[NR + 1]};
+            const float ow = par[NR + 2];
+            const float* __restrict__ tile = reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s);
+            mbar_wait(&full[s], (i / STAGES) & 1);
+
+            float acc[8], acc_ow = 0.f;
+#pragma unroll
+            for (int v = 0; v < 8; ++v) acc[v] = 0.f;
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                int ix, iy;
+                float dl[2];
+                stencil2<float, N_IN>(x[k], R, neg_origin, scale, g, ix, iy, dl);
+                const bool x_lo = (unsigned)ix < (unsigned)g[0], x_hi = (unsigned)(ix + 1) < (unsigned)g[0];
+                const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
+                const int off = iy * g[0] + ix;
+                float G00 = 0.f, G10 = 0.f, G01 = 0.f, G11 = 0.f;
+                if (x_lo && y_lo) G00 = tile[off];
+                if (x_hi && y_lo) G10 = tile[off + 1];
+                if (x_lo && y_hi) G01 = tile[off + g[0]];
+                if (x_hi && y_hi) G11 = tile[off + g[0] + 1];
+                const float du0 = 1.f - dl[0], du1 = 1.f - dl[1];
+                const float s_ = du1 * (du0 * G00 + dl[0] * G10) + dl[1] * (du0 * G01 + dl[0] * G11);
+                const float gx = du1 * (G10 - G00) + dl[1] * (G11 - G01);
+                const float gy = du0 * (G01 - G00) + dl[0] * (G11 - G10);
+                acc_ow += HAS_PW ? s_ * pw[k] : s_;
+                dpw[k] += s_ * ow;
+                const float f = HAS_PW ? ow * pw[k] : ow;
+                const float sx = (f * gx) * scale[0], sy = (f * gy) * scale[1];
+                if constexpr (N_IN == 3) { acc[6] += sx; acc[7] += sy; } else { acc[4] += sx; acc[5] += sy; }
+#pragma unroll
+                for (int j = 0; j < N_IN; ++j) {
+                    acc[2 * j] += sx * x[k][j];
+                    acc[2 * j + 1] += sy * x[k][j];
+                    dpt[k][j] += R[0][j] * sx + R[1][j] * sy;
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);          // this warp is done with the staged image
+            if constexpr (N_IN == 2) acc[6] = acc_ow;
+            butterfly8(acc, lane);
+            if constexpr (N_IN == 3) acc_ow = warp_sum(acc_ow);
+            if ((lane & 3) == 0 && vsel < NV) atomicAdd(&pose_acc[bl * NV + vsel], acc[0]);
+            if constexpr (N_IN == 3) {
+                if (lane == 1) atomicAdd(&pose_acc[bl * NV + NV - 1], acc_ow);
+            }
+        }
+        named_bar_sync(1, kTmaConsumers);
+        for (int i = threadIdx.x; i < n_round * NV; i += kTmaConsumers) {
+            const int bl = i / NV, v = i % NV;
+            const float r = pose_acc[i];
+            const int64_t b = b0 + r0 + bl;
+            if (v < NR) red_add(d_rotation + b * NR + v, r);
+            else if (v < NR + 2) red_add(d_translation + b * 2 + (v - NR), r);
+            else if (d_out_weight) red_add(d_out_weight + b, r);
+        }
+        named_bar_sync(1, kTmaConsumers);      // pose_par / pose_acc are rewritten by the next round
+    }
+
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        int p = (pc * K + k) * kTmaConsumers + (int)threadIdx.x;
+        if (p >= P) continue;
+        if (perm) p = __ldg(perm + p);
+#pragma unroll
+        for (int j = 0; j < N_IN; ++j) red_add(d_points + (int64_t)p * N_IN + j, dpt[k][j]);
+        if (d_point_weight) red_add(d_point_weight + p, dpw[k]);
+    }
+}
+
+inline size_t tma_pullback_smem(int64_t cells, int stages, int n_in) {
+    const int NV = 2 * n_in + 3, PP = (NV + 3) / 4 * 4;
+    const size_t stage_stride = ((size_t)cells * 4 + 127) / 128 * 128;
+    return stage_stride * stages + sizeof(float) * kTmaRound * (PP + NV + 1) + 16 * stages + 64;
+}
+
+}  // namespace dpr

@@ -44,10 +44,14 @@ def test_fast_forward_kernel_has_no_packed_fma():
         pytest.skip("cuobjdump not available")
     chunks = sass.split("Function : ")
     fast = [c for c in chunks if "fwd_tile2d_fast_kernel" in c.split("\n", 1)[0]]
-    assert len(fast) == 4, "expected 4 instantiations of the fast forward kernel"
+    assert len(fast) == 8, "expected 8 instantiations of the fast forward kernel"
     for body in fast:
         assert "FFMA2" not in body
         assert "FMUL2" in body and "ATOMS.ADD" in body
+    tma = [c for c in chunks if "pullback_tma2d_kernel" in c.split("\n", 1)[0]]
+    assert len(tma) == 8
+    for body in tma:   # TMA bulk copy + mbarrier pipeline really are in the SASS, and no packed FMA
+        assert "UBLKCP" in body and "SYNCS" in body and "FFMA2" not in body
     pb = [c for c in chunks if "pullback_gather2d_kernelIf" in c.split("\n", 1)[0]]
     assert len(pb) == 8   # N_in in {2,3} x point weights x paired loads
     for body in pb:

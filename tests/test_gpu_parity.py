@@ -128,10 +128,10 @@ def test_forward_slabs_with_chunk_culling(n_in):
     d["points"][:, :100] *= 4.0          # some points far outside
     out_ref, _ = _oracle_pair(d, grid, np.float32)
     args = dev_args(d, np.float32)
-    with forced(forward_algo=2, tile_smem_bytes=20 * 64 * 4):
+    with forced(forward_algo=2, tile_smem_bytes=20 * 64 * 4, point_split=1):
         out = dpr_b200.raster(grid, *args)
         assert dpr_b200.last_path(0) == "tile2d_slabs_culled_fixed"
-    with forced(forward_algo=2, tile_smem_bytes=20 * 64 * 4, point_sort=2):
+    with forced(forward_algo=2, tile_smem_bytes=20 * 64 * 4, point_sort=2, point_split=1):
         out2 = dpr_b200.raster(grid, *args)
         assert dpr_b200.last_path(0) == "tile2d_slabs_fixed"
     assert rel_l2(to_np(out), out_ref) <= 1e-5 and rel_l2(to_np(out2), out_ref) <= 1e-5
@@ -178,6 +178,24 @@ def test_pullback_pose_chunking(pose_chunk, algo):
         assert dpr_b200.last_path(1).startswith("gather_global" if algo == 1 else "gather2d")
     for k in FIELDS:
         assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-10, k
+
+
+@pytest.mark.parametrize("n_in", [2, 3])
+@pytest.mark.parametrize("weights", [True, False])
+@pytest.mark.parametrize("B,pose_chunk", [(5, 0), (150, 0), (150, 70)])
+def test_pullback_tma_staged_images(n_in, weights, B, pose_chunk):
+    """Float32 pose images that fit shared memory: TMA-staged ring (producer warp + mbarriers), d_background fused
+    into the same read; several 64-pose rounds and several pose chunks; sorted and unsorted points."""
+    grid = (40, 24)
+    d = make_inputs(1234 + B, n_in, 2, 9001, B, grid, np.float32, weights)
+    d["points"][:, :3] = np.array([[5.0, -7.0, 1e30], [0.99, -1.0, 1.0]] + ([[0.0, 0.0, 0.0]] if n_in == 3 else []), dtype=np.float32)
+    _, pb_ref = _oracle_pair(d, grid, np.float32)
+    for sort in (1, 2):
+        with forced(pullback_algo=4, point_sort=sort, pose_chunk=pose_chunk):
+            pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], torch.float32), *dev_args(d, np.float32))
+            assert dpr_b200.last_path(1) == ("tma2d_sorted" if sort == 1 else "tma2d")
+        for k in FIELDS:
+            assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, (sort, k)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
