@@ -261,7 +261,9 @@ def main():
     kernels = {}
     for name, ms in records:
         kernels.setdefault(name, []).append(ms)
-    kernel_ms = {k: sum(v) / len(v) for k, v in kernels.items()}
+    kernel_ms = {k: sum(v) / args.steps for k, v in kernels.items()}            # per step (all launches of the kernel)
+    kernel_launch_ms = {k: sum(v) / len(v) for k, v in kernels.items()}         # per launch
+    launches_per_step = {k: len(v) / args.steps for k, v in kernels.items()}
     fwd_bytes, bwd_bytes = algorithmic_bytes(cfg)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
@@ -276,13 +278,15 @@ def main():
     if bwd_names:
         cand[max(bwd_names, key=kernel_ms.get)] = bwd_bytes
     dom = max(cand, key=lambda k: kernel_ms[k])
-    achieved = cand[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+    bytes_per_launch = cand[dom] / launches_per_step[dom]
+    achieved = bytes_per_launch / (kernel_launch_ms[dom] * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         traffic = json.load(open(tpath)).get(args.config, {}).get(dom)
     roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=traffic, algorithmic_bytes_per_launch=cand[dom], kernel_ms=kernel_ms[dom], peak_source=peak_src,
+                    traffic=traffic, algorithmic_bytes_per_launch=bytes_per_launch, kernel_ms=kernel_launch_ms[dom],
+                    launches_per_step=launches_per_step[dom], peak_source=peak_src,
                     whole_step=dict(algorithmic_bytes=(fwd_bytes if do_fwd else 0) + bwd_bytes,
                                     achieved=((fwd_bytes if do_fwd else 0) + bwd_bytes) / (ms_per_step * 1e-3) / 1e9,
                                     frac=((fwd_bytes if do_fwd else 0) + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak))

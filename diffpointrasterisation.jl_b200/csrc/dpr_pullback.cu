@@ -225,7 +225,7 @@ static bool use_sort(const PullbackArgs<T>& a) {
     const SortPlan sp = make_sort_plan(a.n_in, a.P, (int)sizeof(T), a.point_weight != nullptr, 256);
     if (!a.workspace || a.workspace_bytes < sp.total) return false;
     if (tuning().point_sort == 1) return true;
-    return a.P >= 4096 && a.B >= 4;
+    return a.P >= 4096 && a.B >= 4 && a.P * a.B >= ((int64_t)1 << 22);   // three extra launches must pay for themselves
 }
 
 template <typename T, int N_IN, int N_OUT>

@@ -94,7 +94,7 @@ def test_forward_paths_agree(dtype, algo, opts):
         path = dpr_b200.last_path(0)
     assert rel_l2(to_np(out), out_ref) <= TOL[dtype], path
     if algo == 1:
-        assert path == "global_redg"
+        assert path.startswith("global_redg")
     else:
         assert path.startswith("tile2d"), path
 
