@@ -216,7 +216,13 @@ def main():
     ds_dout = dpr_b200.empty_f(grid + (B,), td, dev)
     ds_dout.normal_(generator=gen)
     out = dpr_b200.empty_f(grid + (B,), td, dev)
-    drv = sharded.PoseShardedRaster()
+    comm, comm_kind = None, "none"
+    if world > 1:
+        try:
+            comm, comm_kind = sharded.DprComm(dev), "dpr_comm_allreduce_sum (NCCL via libdpr.so)"
+        except Exception as e:   # NCCL could not be resolved inside the library: torch.distributed does the all-reduce
+            comm, comm_kind = None, f"torch.distributed all_reduce ({type(e).__name__})"
+    drv = sharded.PoseShardedRaster(comm=comm)
     do_fwd = "fwd" in cfg["ops"]
 
     def step():
@@ -363,6 +369,7 @@ def main():
                     data="synthetic",
                     config=dict(workload=f"{args.config}: {cfg['label']}", ops=cfg["ops"], poses_per_gpu=B,
                                 parallelism=f"pose-sharded x{world}, points replicated, 1 all-reduce of d_points+d_point_weight",
+                                collective=comm_kind,
                                 l2="inputs larger than L2 (out and ds_dout are 1.07 GB each per step; no flush needed)",
                                 forward_path=dpr_b200.last_path(0), pullback_path=dpr_b200.last_path(1)),
                     kernels_ms=kernel_ms, fwd_splats_per_s=(P * B * world / (sum(kernel_ms[k] for k in kernel_ms if k.startswith("fwd_") or k == "fill_background") * 1e-3)) if do_fwd else None,

@@ -21,6 +21,7 @@ SYMBOLS = [
     "dpr_raster_pullback_host_f64", "dpr_host_alloc", "dpr_host_free", "dpr_host_release",
     "dpr_set_option", "dpr_get_option", "dpr_kernel_launch_count", "dpr_last_path",
     "dpr_profile_enable", "dpr_profile_count", "dpr_profile_get",
+    "dpr_comm_unique_id", "dpr_comm_init_rank", "dpr_comm_destroy", "dpr_comm_allreduce_sum_f32", "dpr_comm_allreduce_sum_f64",
 ]
 
 OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM, OPT_POINT_SORT = range(7)
@@ -78,6 +79,16 @@ def load() -> ctypes.CDLL:
     lib.dpr_profile_count.restype = c_i
     lib.dpr_profile_get.restype = c_i
     lib.dpr_profile_get.argtypes = [c_i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(ctypes.c_float)]
+    lib.dpr_comm_unique_id.restype = c_i
+    lib.dpr_comm_unique_id.argtypes = [c_p]
+    lib.dpr_comm_init_rank.restype = c_i
+    lib.dpr_comm_init_rank.argtypes = [ctypes.POINTER(c_p), c_i, c_i, c_p]
+    lib.dpr_comm_destroy.restype = c_i
+    lib.dpr_comm_destroy.argtypes = [c_p]
+    for suf in ("f32", "f64"):
+        f = getattr(lib, f"dpr_comm_allreduce_sum_{suf}")
+        f.restype = c_i
+        f.argtypes = [c_p, c_p, c_i64, c_p]
     lib.dpr_last_path.restype = ctypes.c_char_p
     lib.dpr_last_path.argtypes = [c_i]
     _lib = lib

@@ -46,6 +46,8 @@ static void profile_clear() {
     g_prof.clear();
 }
 
+void set_error_message(const char* msg) { snprintf(tl_error, sizeof(tl_error), "%s", msg); }
+
 int cuda_fail(cudaError_t e, const char* what) {
     snprintf(tl_error, sizeof(tl_error), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     cudaGetLastError();  // clear the sticky-free error state

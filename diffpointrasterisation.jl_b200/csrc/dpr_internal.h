@@ -39,6 +39,7 @@ struct LaunchScope {
 };
 void set_last_path(int op, const char* name);
 int cuda_fail(cudaError_t e, const char* what);     // records the message, returns DPR_ERR_CUDA
+void set_error_message(const char* msg);            // thread-local text behind dpr_last_error_message()
 
 #define DPR_CUDA_TRY(expr)                                              \
     do {                                                                \

@@ -36,14 +36,49 @@ def shard_poses(t: Optional[torch.Tensor], rank: int, world_size: int) -> Option
     return t[..., lo:hi]
 
 
+class DprComm:
+    """The library's own communicator (dpr_comm_*, include/dpr.h): NCCL resolved inside libdpr.so.  torch.distributed
+    is only used to ship the 128-byte unique id from rank 0 to the other ranks."""
+
+    def __init__(self, device, group: Optional[dist.ProcessGroup] = None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib
+        self.lib = _lib.load()
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        ident = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            _lib.check(self.lib.dpr_comm_unique_id(ctypes.cast(buf, ctypes.c_void_p)))
+            ident = torch.tensor(list(buf), dtype=torch.uint8)
+        ident = ident.to(device)
+        dist.broadcast(ident, src=0, group=group)
+        raw = bytes(ident.cpu().tolist())
+        self.handle = ctypes.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(self.lib.dpr_comm_init_rank(ctypes.byref(self.handle), world, rank, raw))
+        self.device = device
+
+    def all_reduce_(self, t: torch.Tensor) -> None:
+        fn = self.lib.dpr_comm_allreduce_sum_f32 if t.dtype == torch.float32 else self.lib.dpr_comm_allreduce_sum_f64
+        with torch.cuda.device(t.device):
+            self._lib.check(fn(self.handle, t.data_ptr(), t.numel(), torch.cuda.current_stream(t.device).cuda_stream))
+
+    def close(self) -> None:
+        if self.handle:
+            self.lib.dpr_comm_destroy(self.handle)
+            self.handle = None
+
+
 class PoseShardedRaster:
     def __init__(self, group: Optional[dist.ProcessGroup] = None, forward_fn: Callable = None,
-                 pullback_fn: Callable = None):
+                 pullback_fn: Callable = None, comm: Optional[DprComm] = None):
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
         self.forward_fn = forward_fn or interface.raster
         self.pullback_fn = pullback_fn
+        self.comm = comm          # None: torch.distributed all_reduce; DprComm: the library's NCCL entry point
         self._packed = None
 
     # ---- forward: no collective --------------------------------------------------------------------------
@@ -77,5 +112,8 @@ class PoseShardedRaster:
             res = PullbackResult(d_points, res.rotation, res.translation, res.background, res.out_weight, d_pw)
         work = None
         if self.world_size > 1:
-            work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
+            if self.comm is not None:
+                self.comm.all_reduce_(packed)          # enqueued on the current stream, like the kernels
+            else:
+                work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=self.group, async_op=async_op)
         return res, work

@@ -111,6 +111,19 @@ int dpr_host_alloc(void** ptr, size_t bytes);  /* pinned host memory */
 int dpr_host_free(void* ptr);
 int dpr_host_release(void);                    /* frees the staging arena of the current device */
 
+/* Multi-GPU (new; the reference is single-device): one process per GPU, poses sharded contiguously, points
+ * replicated.  The forward needs no exchange; the pullback needs ONE sum over ranks of the pose-summed gradients
+ * d_points (src/raster_pullback.jl:141) and d_point_weight (:146), which callers keep in one packed (N_in+1)*P buffer.
+ * Rank 0 creates a 128-byte id (ncclUniqueId), ships it to the other ranks by any means, every rank calls
+ * dpr_comm_init_rank, then dpr_comm_allreduce_sum_* after its local dpr_raster_pullback_* on the same stream.
+ * NCCL is loaded with dlopen at first use; DPR_ERR_NCCL if it is not available. */
+typedef struct dpr_comm* dpr_comm_t;
+int dpr_comm_unique_id(void* id128);
+int dpr_comm_init_rank(dpr_comm_t* comm, int n_ranks, int rank, const void* id128);
+int dpr_comm_destroy(dpr_comm_t comm);
+int dpr_comm_allreduce_sum_f32(dpr_comm_t comm, float* buf, int64_t count, dpr_stream_t stream);
+int dpr_comm_allreduce_sum_f64(dpr_comm_t comm, double* buf, int64_t count, dpr_stream_t stream);
+
 /* Introspection / tuning (benchmarks and tests). */
 enum dpr_option {
     DPR_OPT_FORWARD_ALGO = 0,   /* 0 auto, 1 global-reduction kernel, 2 shared-memory tile kernel            */
