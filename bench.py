@@ -119,6 +119,14 @@ class ClockSampler(threading.Thread):
                     samples=len(self.samples))
 
 
+def host_threads():
+    """Cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not shrink the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_port_time(cfg, inputs, n_poses, threads, steps=1, ds_dout=None):
     """Times the oracle port (the reference's CPU algorithm restated in C + OpenMP, same parallel structure:
     src/raster_pullback.jl:115-146) on the first n_poses poses.  Returns seconds per step (fwd, bwd)."""
@@ -147,8 +155,7 @@ def run_reference(args, cfg):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import oracle
-    threads = oracle.max_threads()
+    threads = host_threads()
     inputs = synth_inputs(cfg, 1000 + int(args.config[-1]), 0)
     n_poses = min(cfg["B"], max(threads, args.ref_poses))
     dt = np.float32 if cfg["dtype"] == "f32" else np.float64
@@ -354,8 +361,7 @@ def main():
 
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu:
-        from oracle import oracle
-        threads = oracle.max_threads()
+        threads = host_threads()
         n_poses = min(B, args.cpu_poses)
         cpu_port_time(cfg, inputs, min(n_poses, threads), threads)  # warm the threads
         tf, tb = cpu_port_time(cfg, inputs, n_poses, threads)
