@@ -1,0 +1,91 @@
+"""Full-size (BASELINE.json) runs on the GPU, checked through size-independent properties and pose subsets.
+
+The oracle cannot redo 4e8..2e9 splats in a test, but poses are independent: a handful of poses of the full-size run
+are compared with the oracle directly, the pose-summed gradients are checked by linearity over pose shards, and the
+forward and the pullback are tied together by the adjoint identities
+    <ds_dout_b, out_b - background_b> = out_weight_b * d_out_weight_b          (out - bg is linear in out_weight)
+    sum_p point_weight_p * d_point_weight_p = sum_b out_weight_b * d_out_weight_b
+    d_background_b = sum(ds_dout_b).
+"""
+import numpy as np
+import pytest
+import torch
+
+import dpr_b200
+from oracle import oracle
+from tests.helpers import random_rotations, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _full_inputs(n_in, P, B, grid, seed, weights):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    pts = np.asfortranarray((0.4 * rng.standard_normal((n_in, P))).astype(np.float32))
+    rot = random_rotations(rng, n_in, 2, B, np.float32)
+    tr = np.asfortranarray((0.1 * rng.standard_normal((2, B))).astype(np.float32))
+    bg = np.arange(1, B + 1, dtype=np.float32) if weights else None
+    ow = (10 * rng.random(B)).astype(np.float32) if weights else None
+    w = rng.random(P)
+    pw = (w / w.sum() * P).astype(np.float32) if weights else None     # mean 1 keeps magnitudes comparable
+    return pts, rot, tr, bg, ow, pw
+
+
+def _dev(a):
+    return None if a is None else dpr_b200.fortran(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+
+
+@pytest.mark.parametrize("name,n_in,P,B,grid,weights,do_fwd", [
+    ("cfg2", 3, 100_000, 4096, (256, 256), False, True),
+    ("cfg2w", 3, 100_000, 512, (256, 256), True, True),
+    ("cfg5", 3, 1_000_000, 2048, (128, 128), False, False),
+])
+def test_full_size_properties(name, n_in, P, B, grid, weights, do_fwd):
+    pts, rot, tr, bg, ow, pw = _full_inputs(n_in, P, B, grid, 2000 + len(name), weights)
+    d = [_dev(a) for a in (pts, rot, tr, bg, ow, pw)]
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    ds = dpr_b200.empty_f(grid + (B,), torch.float32, "cuda")
+    ds.normal_(generator=gen)
+    pb = dpr_b200.raster_pullback_(ds, *d)
+    ow_t = d[4] if weights else torch.ones(B, device="cuda")
+    pw_t = d[5] if weights else torch.ones(P, device="cuda")
+    # d_background = sum(ds_dout) per pose
+    ref_bg = ds.double().sum(dim=tuple(range(len(grid))))
+    assert rel_l2(pb.background.cpu().numpy(), ref_bg.cpu().numpy()) < 1e-5
+    # sum_p pw_p d_pw_p == sum_b ow_b d_ow_b
+    lhs = float((pw_t.double() * pb.point_weight.double()).sum())
+    rhs = float((ow_t.double() * pb.out_weight.double()).sum())
+    assert abs(lhs - rhs) <= 2e-4 * max(abs(lhs), abs(rhs), float(pb.out_weight.double().abs().sum()) * 1e-2), (lhs, rhs)
+    # pose subsets against the oracle (per-pose gradients) and linearity of the pose-summed gradients over shards
+    sel = np.array([0, 1, B // 3, B // 2, B - 2, B - 1])
+    sub = lambda a: None if a is None else np.asfortranarray(a[..., sel])
+    ds_sub = np.asfortranarray(ds[..., torch.from_numpy(sel).cuda()].cpu().numpy())
+    ref = oracle.raster_pullback(ds_sub, pts, sub(rot), sub(tr), sub(bg), sub(ow), pw, dtype=np.float32, n_slabs=6, f64_accumulate=True)
+    for k in ("rotation", "translation", "background", "out_weight"):
+        got = getattr(pb, k).cpu().numpy()[..., sel]
+        assert rel_l2(got, getattr(ref, k)) <= 1e-5, (name, k)
+    half = B // 2
+    sh = lambda t, lo, hi: None if t is None else dpr_b200.fortran(t[..., lo:hi])
+    acc_p = torch.zeros_like(pb.points, dtype=torch.float64)
+    acc_w = torch.zeros_like(pb.point_weight, dtype=torch.float64)
+    for lo, hi in ((0, half), (half, B)):
+        part = dpr_b200.raster_pullback_(sh(ds, lo, hi), d[0], sh(d[1], lo, hi), sh(d[2], lo, hi), sh(d[3], lo, hi), sh(d[4], lo, hi), d[5])
+        acc_p += part.points.double()
+        acc_w += part.point_weight.double()
+    assert rel_l2(pb.points.cpu().numpy(), acc_p.cpu().numpy()) <= 1e-5
+    assert rel_l2(pb.point_weight.cpu().numpy(), acc_w.cpu().numpy()) <= 1e-5
+    # the pose-summed d_points of the 6-pose subset alone must equal the oracle's (checks the d_points arithmetic)
+    part = dpr_b200.raster_pullback_(_dev(ds_sub), d[0], _dev(sub(rot)), _dev(sub(tr)), _dev(sub(bg)), _dev(sub(ow)), d[5])
+    assert rel_l2(part.points.cpu().numpy(), ref.points) <= 1e-5
+    assert rel_l2(part.point_weight.cpu().numpy(), ref.point_weight) <= 1e-5
+    if not do_fwd:
+        return
+    out = dpr_b200.raster(grid, *d)
+    ref_out = oracle.raster(grid, pts, sub(rot), sub(tr), sub(bg), sub(ow), pw, dtype=np.float32, n_threads=6, f64_accumulate=True)
+    assert rel_l2(out[..., torch.from_numpy(sel).cuda()].cpu().numpy(), ref_out) <= 1e-5
+    # adjoint identity per pose: <ds_dout_b, out_b - bg_b> = ow_b * d_ow_b
+    bg_t = d[3] if weights else torch.zeros(B, device="cuda")
+    dims = tuple(range(len(grid)))
+    inner = (ds.double() * (out.double() - bg_t.double().reshape((1,) * len(grid) + (B,)))).sum(dim=dims)
+    want = ow_t.double() * pb.out_weight.double()
+    scale = float(want.abs().mean())
+    assert float((inner - want).abs().max()) <= 5e-4 * scale + 1e-6, name

@@ -272,6 +272,42 @@ def test_edge_cases():
         np.testing.assert_allclose(to_np(getattr(pbe, k)), getattr(ref, k), atol=1e-12, err_msg=k)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (40, 24)), (2, 2, (33, 17)), (3, 3, (12, 10, 8))])
+def test_no_out_of_bounds_writes(dtype, n_in, n_out, grid):
+    """compute-sanitizer is not available on the GPU pool, so guard the outputs instead: every output buffer sits
+    inside a larger buffer filled with a sentinel; points cluster on the image borders and far outside."""
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    P, B, pad = 6000, 21, 4096
+    d = make_inputs(4242, n_in, n_out, P, B, grid, dtype)
+    d["points"][:, ::3] *= 2.6                     # a third of the points outside / on the borders
+    d["points"][:, :5] = 1e20
+    args = dev_args(d, dtype)
+    ds = to_dev(d["ds_dout"], td)
+    sentinel = 12345.0
+
+    def guarded(shape):
+        n = int(np.prod(shape))
+        buf = torch.full((n + 2 * pad,), sentinel, dtype=td, device="cuda")
+        view = buf[pad:pad + n].view(tuple(shape)[::-1]).permute(*range(len(shape) - 1, -1, -1))
+        return buf, view
+
+    for falgo in (1, 2):
+        buf, out = guarded(tuple(grid) + (B,))
+        with forced(forward_algo=falgo):
+            dpr_b200.raster_(out, *args)
+        assert torch.all(buf[:pad] == sentinel) and torch.all(buf[-pad:] == sentinel), f"forward algo {falgo} wrote out of bounds"
+    palgos = (1, 2, 3, 4) if (n_out == 2 and dtype == np.float32) else ((1, 2) if n_out == 2 else (1,))
+    for palgo in palgos:
+        shapes = dict(points_out=(n_in, P), rotation_out=(n_out, n_in, B), translation_out=(n_out, B),
+                      background_out=(B,), out_weight_out=(B,), point_weight_out=(P,))
+        bufs = {k: guarded(v) for k, v in shapes.items()}
+        with forced(pullback_algo=palgo):
+            dpr_b200.raster_pullback_(ds, *args, **{k: v[1] for k, v in bufs.items()})
+        for k, (buf, _) in bufs.items():
+            assert torch.all(buf[:pad] == sentinel) and torch.all(buf[-pad:] == sentinel), f"pullback algo {palgo}: {k} out of bounds"
+
+
 def test_errors_mirror_reference():
     grid = (8, 8)
     d = make_inputs(9, 3, 2, 10, 2, grid, np.float64)
