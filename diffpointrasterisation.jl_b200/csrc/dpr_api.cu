@@ -85,7 +85,7 @@ int current_device_info(DeviceInfo& info) {
 
 static int check_dims(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B) {
     if (!grid) return DPR_ERR_NULL_POINTER;
-    if (!((n_in == 2 && n_out == 2) || (n_in == 3 && n_out == 2) || (n_in == 3 && n_out == 3))) return DPR_ERR_UNSUPPORTED;
+    if (n_in < 1 || n_in > 3 || n_out < 1 || n_out > n_in) return DPR_ERR_UNSUPPORTED;   // any N_out <= N_in <= 3
     if (P < 0 || B < 0) return DPR_ERR_BAD_DIMS;
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) {
@@ -385,7 +385,7 @@ const char* dpr_status_string(int status) {
     switch (status) {
         case DPR_OK: return "ok";
         case DPR_ERR_BAD_DIMS: return "bad dimensions (negative size, grid extent < 1, or size overflow)";
-        case DPR_ERR_UNSUPPORTED: return "unsupported (N_in, N_out) or element type; supported: (2,2), (3,2), (3,3) in f32/f64";
+        case DPR_ERR_UNSUPPORTED: return "unsupported (N_in, N_out) or element type; supported: 1 <= N_out <= N_in <= 3 in f32/f64";
         case DPR_ERR_NULL_POINTER: return "a required pointer is NULL";
         case DPR_ERR_WORKSPACE: return "workspace smaller than dpr_workspace_bytes()";
         case DPR_ERR_CUDA: return "CUDA runtime error (see dpr_last_error_message)";

@@ -584,6 +584,9 @@ int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
     if (a.n_in == 2 && a.n_out == 2) return forward_global<T, 2, 2>(a, dev);
     if (a.n_in == 3 && a.n_out == 2) return forward_global<T, 3, 2>(a, dev);
     if (a.n_in == 3 && a.n_out == 3) return forward_global<T, 3, 3>(a, dev);
+    if (a.n_in == 1 && a.n_out == 1) return forward_global<T, 1, 1>(a, dev);
+    if (a.n_in == 2 && a.n_out == 1) return forward_global<T, 2, 1>(a, dev);
+    if (a.n_in == 3 && a.n_out == 1) return forward_global<T, 3, 1>(a, dev);
     return DPR_ERR_UNSUPPORTED;
 }
 

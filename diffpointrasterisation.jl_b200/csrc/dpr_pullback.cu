@@ -456,6 +456,9 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     if (a.n_in == 2 && a.n_out == 2) return pullback_global<T, 2, 2>(a, dev);
     if (a.n_in == 3 && a.n_out == 2) return pullback_global<T, 3, 2>(a, dev);
     if (a.n_in == 3 && a.n_out == 3) return pullback_global<T, 3, 3>(a, dev);
+    if (a.n_in == 1 && a.n_out == 1) return pullback_global<T, 1, 1>(a, dev);
+    if (a.n_in == 2 && a.n_out == 1) return pullback_global<T, 2, 1>(a, dev);
+    if (a.n_in == 3 && a.n_out == 1) return pullback_global<T, 3, 1>(a, dev);
     return DPR_ERR_UNSUPPORTED;
 }
 

@@ -41,8 +41,9 @@ __device__ __forceinline__ uint32_t morton_key(const T* __restrict__ points, int
         c = fminf(fmaxf(c, 0.f), cells - 1.f);
         q[j] = (uint32_t)c;
     }
-    if (N_IN == 2) return part1by1(q[0]) | (part1by1(q[1]) << 1);
-    return part1by2(q[0]) | (part1by2(q[1]) << 1) | (part1by2(q[2]) << 2);
+    if constexpr (N_IN == 1) return q[0];
+    else if constexpr (N_IN == 2) return part1by1(q[0]) | (part1by1(q[1]) << 1);
+    else return part1by2(q[0]) | (part1by2(q[1]) << 1) | (part1by2(q[2]) << 2);
 }
 
 template <typename T, int N_IN>

@@ -128,8 +128,25 @@ def _stream_handle(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _scalar_to_vec(v, dtype, device):
+    """Single-image scalars (background::Number, out_weight::Number) -> length-1 vectors (src/interface.jl:100-120)."""
+    if v is None:
+        return None
+    if isinstance(v, torch.Tensor):
+        return v.reshape(1).to(device=device, dtype=dtype)
+    return torch.tensor([float(v)], dtype=dtype, device=device)
+
+
+def _is_single_image(rotation) -> bool:
+    return isinstance(rotation, torch.Tensor) and rotation.dim() == 2
+
+
 def raster_(out: torch.Tensor, points, rotation, translation, background=None, out_weight=None, point_weight=None):
-    """`raster!(out, points, rotation, translation, [background, out_weight, point_weight])`, batched.
+    """`raster!(out, points, rotation, translation, [background, out_weight, point_weight])`.
+
+    Batched when `rotation` is (N_out, N_in, B); single image when it is a matrix (N_out, N_in) - then `translation` is
+    (N_out,), `background` / `out_weight` are numbers and `out` has no batch axis: exactly the wrapper of
+    src/interface.jl:100-120 (a batch of one with a singleton trailing dimension, src/util.jl:98-102).
 
     `out` is (g_1..g_n, B) column-major and is overwritten (src/raster.jl:27).  Missing optional arguments are the
     reference's defaults: background 0, out_weight 1, point_weight 1 (src/interface.jl:87-92, :368-394).
@@ -138,6 +155,12 @@ def raster_(out: torch.Tensor, points, rotation, translation, background=None, o
         raise RuntimeError("out is not a CUDA tensor: this library has no CPU path")
     if not is_fortran(out):
         raise ValueError("out must have column-major strides (use empty_f)")
+    if _is_single_image(rotation):
+        if translation.dim() != 1 or translation.shape[0] != rotation.shape[0]:
+            raise DimensionMismatch(f"Dimension of translation ({tuple(translation.shape)}) and number of rows of rotation ({rotation.shape[0]}) do not match")
+        raster_(out.unsqueeze(-1), points, rotation.unsqueeze(-1), translation.unsqueeze(-1),
+                _scalar_to_vec(background, out.dtype, out.device), _scalar_to_vec(out_weight, out.dtype, out.device), point_weight)
+        return out
     dtype, device = out.dtype, out.device
     suf = _suffix(dtype)
     n_out_p1 = out.dim()
@@ -170,8 +193,11 @@ def raster(grid_size: Sequence[int], points, rotation, translation, background=N
     for t in (rotation, translation, background, out_weight, point_weight):
         if isinstance(t, torch.Tensor):
             dtype = torch.promote_types(dtype, t.dtype)
+    if rotation.dim() == 2:     # single image (src/interface.jl:100-120)
+        out = empty_f(tuple(grid_size), dtype, points.device)
+        return raster_(out, points, rotation, translation, background, out_weight, point_weight)
     if rotation.dim() != 3:
-        raise DimensionMismatch("rotation must be (N_out, N_in, B)")
+        raise DimensionMismatch("rotation must be (N_out, N_in, B) or, for a single image, (N_out, N_in)")
     B = rotation.shape[-1]
     out = empty_f(tuple(grid_size) + (B,), dtype, points.device)
     return raster_(out, points, rotation, translation, background, out_weight, point_weight)
@@ -191,6 +217,19 @@ def raster_pullback_(ds_dout: torch.Tensor, points, rotation, translation, backg
     """
     if not ds_dout.is_cuda:
         raise RuntimeError("ds_dout is not a CUDA tensor: this library has no CPU path")
+    if _is_single_image(rotation):
+        # Single image.  The reference's CUDA extension only has an error stub for it
+        # (ext/DiffPointRasterisationCUDAExt.jl:213-228); the batch kernels handle B = 1 by splitting the points over
+        # the SMs, so route it through a batch of one and drop the batch axis of the per-pose results
+        # (same field meaning as the CPU method src/raster_pullback.jl:74-81).
+        if any(v is not None for v in (rotation_out, translation_out, background_out, out_weight_out)):
+            raise ValueError("pre-allocated per-pose outputs are only supported in batch mode")
+        res = raster_pullback_(ds_dout.unsqueeze(-1), points, rotation.unsqueeze(-1), translation.unsqueeze(-1),
+                               _scalar_to_vec(background, ds_dout.dtype, ds_dout.device),
+                               _scalar_to_vec(out_weight, ds_dout.dtype, ds_dout.device), point_weight,
+                               points_out=points_out, point_weight_out=point_weight_out)
+        return PullbackResult(res.points, res.rotation[..., 0], res.translation[..., 0], res.background[0],
+                              res.out_weight[0], res.point_weight)
     dtype, device = ds_dout.dtype, ds_dout.device
     for t in (points, rotation, translation, out_weight, point_weight):
         if isinstance(t, torch.Tensor):

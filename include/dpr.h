@@ -17,7 +17,7 @@
  * then accumulates: ext/DiffPointRasterisationCUDAExt.jl:272-276; forward overwrites with the background,
  * src/raster.jl:27), so callers need not pre-zero.  All work is enqueued on `stream`; nothing synchronises.
  *
- * Supported: T in {float, double}; (N_in, N_out) in {(2,2), (3,2), (3,3)}.
+ * Supported: T in {float, double}; any 1 <= N_out <= N_in <= 3 (tuned kernels for the 2-d outputs (2,2) and (3,2)).
  * Return value: DPR_OK (0) or a negative dpr_status; never throws, never aborts.
  */
 #ifndef DPR_H

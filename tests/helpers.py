@@ -21,7 +21,7 @@ def random_rotations(rng, n_in, n_out, B, dtype):
         a = rng.standard_normal((n_in, n_in))
         q, r = np.linalg.qr(a)
         q = q * np.sign(np.diag(r))
-        if np.linalg.det(q) < 0:
+        if n_in > 1 and np.linalg.det(q) < 0:
             q[:, 0] = -q[:, 0]
         out[:, :, b] = q[:n_out, :]
     return out

@@ -77,6 +77,7 @@ def test_argument_validation_without_gpu():
     grid = (ctypes.c_int64 * 2)(8, 8)
     f = lib.dpr_raster_forward_f32
     assert f(4, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2   # unsupported dims
+    assert f(2, 3, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2   # N_out > N_in
     assert f(3, 2, grid, -1, 1, None, None, None, None, None, None, None, None, 0, None) == -1  # bad dims
     assert f(3, 2, (ctypes.c_int64 * 2)(0, 8), 1, 1, None, None, None, None, None, None, None, None, 0, None) == -1
     assert f(3, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -3   # NULL pointers

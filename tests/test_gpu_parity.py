@@ -70,7 +70,8 @@ def test_pullback_readme_known_answer(golden):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
-@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (64, 48)), (3, 3, (24, 20, 16)), (2, 2, (40, 56))])
+@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (64, 48)), (3, 3, (24, 20, 16)), (2, 2, (40, 56)),
+                                             (1, 1, (50,)), (2, 1, (37,)), (3, 1, (64,))])
 @pytest.mark.parametrize("weights", [True, False])
 def test_parity_random(dtype, n_in, n_out, grid, weights):
     """Same distributions as the reference's CUDA tests (test/cuda.jl:10-73 with test/data.jl fixtures)."""
@@ -306,6 +307,32 @@ def test_no_out_of_bounds_writes(dtype, n_in, n_out, grid):
             dpr_b200.raster_pullback_(ds, *args, **{k: v[1] for k, v in bufs.items()})
         for k, (buf, _) in bufs.items():
             assert torch.all(buf[:pad] == sentinel) and torch.all(buf[-pad:] == sentinel), f"pullback algo {palgo}: {k} out of bounds"
+
+
+def test_single_image_interface(golden):
+    """Single-image methods (src/interface.jl:100-120): matrix rotation, vector translation, scalar background and
+    out_weight, no batch axis.  The reference's GPU extension errors for the single-image pullback
+    (ext/DiffPointRasterisationCUDAExt.jl:213-228); here it runs through the batch kernels with B = 1."""
+    for case in golden["forward"]:
+        pts = to_dev(np.asarray(case["points"], dtype=np.float64).T)
+        rot = to_dev(np.asarray(case["rotation"], dtype=np.float64))
+        tr = to_dev(np.asarray(case["translation"], dtype=np.float64))
+        pw = None if case["point_weight"] is None else to_dev(np.asarray(case["point_weight"], dtype=np.float64))
+        out = dpr_b200.raster(tuple(case["grid_size"]), pts, rot, tr, case["background"], case["out_weight"], pw)
+        assert out.shape == (5, 5)
+        np.testing.assert_allclose(to_np(out), np.asarray(case["expected"], dtype=np.float64), atol=1e-12, err_msg=case["name"])
+    g = golden["pullback"]
+    pb = dpr_b200.raster_pullback_(to_dev(np.asarray(g["ds_dout"])), to_dev(np.asarray(g["points"]).T),
+                                   to_dev(np.asarray(g["rotation"])), to_dev(np.asarray(g["translation"])))
+    assert pb.rotation.shape == (2, 2) and pb.translation.shape == (2,) and pb.background.dim() == 0
+    np.testing.assert_allclose(to_np(pb.points), np.asarray(g["d_points"]), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(to_np(pb.rotation), np.asarray(g["d_rotation"]), rtol=2e-5, atol=2e-5)
+    np.testing.assert_allclose(to_np(pb.translation), np.asarray(g["d_translation"]), rtol=2e-5, atol=2e-5)
+    # a big single image (README.md:193 row, scaled): 10^5 points into one 128^3 volume
+    d = make_inputs(8, 3, 3, 100000, 1, (128, 128, 128), np.float32, False)
+    out = dpr_b200.raster((128, 128, 128), to_dev(d["points"]), to_dev(d["rotation"][..., 0]), to_dev(d["translation"][..., 0]))
+    ref = oracle.raster((128, 128, 128), d["points"], d["rotation"], d["translation"], dtype=np.float32, f64_accumulate=True)
+    assert rel_l2(to_np(out), ref[..., 0]) <= 1e-5
 
 
 def test_errors_mirror_reference():
