@@ -38,6 +38,15 @@ CONFIGS = {
                  label="2d->2d, 1M points x 1024 poses, 512x512, Float32, point weights + background"),
     "cfg5": dict(n_in=3, n_out=2, P=1_000_000, B=2048, grid=(128, 128), dtype="f32", weights=False, ops="bwd",
                  label="3d->2d pullback-only, 1M points x 2048 poses per GPU (16384 over 8 GPUs), 128x128, Float32"),
+    # the other rows of the reference's README "Timings" table (README.md:189-193; element type not stated: Float64 here)
+    "readme2": dict(n_in=3, n_out=2, P=10_000, B=64, grid=(1024, 1024), dtype="f64", weights=False, ops="fwd+bwd",
+                    label="README.md:190: 3d->2d, 10k points x 64 images, 1024x1024, Float64"),
+    "readme3": dict(n_in=3, n_out=2, P=100_000, B=64, grid=(128, 128), dtype="f64", weights=False, ops="fwd+bwd",
+                    label="README.md:191: 3d->2d, 100k points x 64 images, 128x128, Float64"),
+    "readme4": dict(n_in=3, n_out=2, P=100_000, B=64, grid=(1024, 1024), dtype="f64", weights=False, ops="fwd+bwd",
+                    label="README.md:192: 3d->2d, 100k points x 64 images, 1024x1024, Float64"),
+    "readme5": dict(n_in=3, n_out=3, P=100_000, B=1, grid=(1024, 1024, 1024), dtype="f64", weights=False, ops="fwd+bwd",
+                    label="README.md:193: 3d->3d, 100k points x 1 image, 1024^3, Float64"),
 }
 METRIC = "splats/sec (points x poses), forward + pullback"
 UNIT = "splats/s"
@@ -213,7 +222,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     td = torch.float32 if cfg["dtype"] == "f32" else torch.float64
-    seed = 1000 + int(args.config[-1])
+    seed = 1000 + int(args.config[-1]) + (100 if args.config.startswith("readme") else 0)
     inputs = synth_inputs(cfg, seed, rank)
     f = lambda a: None if a is None else dpr_b200.fortran(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
     points, rotation, translation = f(inputs["points"]), f(inputs["rotation"]), f(inputs["translation"])

@@ -228,6 +228,14 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
         for (int i = 0; i < NSTREAM; ++i) { have = ar->slot_bytes; rc = arena_reserve(ar->slot[i], have, need); if (rc != DPR_OK) return rc; }
         ar->slot_bytes = have;
     }
+    {   // per-stream kernel workspace (point statistics, spatially sorted copy of the points)
+        const size_t need_ws = forward_workspace_bytes(n_in, n_out, grid, P, cb, (int)sizeof(T));
+        if (need_ws > ar->ws_bytes) {
+            size_t have = 0;
+            for (int i = 0; i < NSTREAM; ++i) { have = ar->ws_bytes; rc = arena_reserve(ar->ws[i], have, need_ws); if (rc != DPR_OK) return rc; }
+            ar->ws_bytes = have;
+        }
+    }
     T* d_points = static_cast<T*>(ar->shared);
     T* d_pw = reinterpret_cast<T*>(static_cast<char*>(ar->shared) + pts_bytes);
     cudaStream_t s0 = ar->streams[0];

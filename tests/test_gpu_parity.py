@@ -380,3 +380,34 @@ SCALED_CONFIGS = [   # BASELINE.json configs, scaled to sizes the oracle finishe
 def test_baseline_configs_scaled(name, n_in, n_out, P, B, grid, dtype, weights):
     d = make_inputs(1000 + int(name[-1]), n_in, n_out, P, B, grid, dtype, weights)
     _check(d, grid, dtype, name)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("n_in,n_out,grid,B", [(3, 2, (64, 64), 300), (2, 2, (48, 32), 17), (3, 3, (16, 16, 16), 40)])
+def test_host_buffer_entry_points(dtype, n_in, n_out, grid, B):
+    """dpr_raster_*_host_*: same results from HOST buffers (pose chunks pipelined over three streams through the
+    library's staging arena), including the pose-sum of d_points across chunks."""
+    import ctypes
+    from dpr_b200 import _lib
+    lib = _lib.load()
+    suf = "f32" if dtype == np.float32 else "f64"
+    P = 20000
+    d = make_inputs(321, n_in, n_out, P, B, grid, dtype)
+    out_ref, pb_ref = _oracle_pair(d, grid, dtype)
+    f = lambda a: np.asfortranarray(a)
+    h = {k: f(d[k]) for k in ("points", "rotation", "translation", "background", "out_weight", "point_weight", "ds_dout")}
+    ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    garr = (ctypes.c_int64 * n_out)(*grid)
+    out = np.empty(tuple(grid) + (B,), dtype=dtype, order="F")
+    _lib.check(getattr(lib, f"dpr_raster_forward_host_{suf}")(n_in, n_out, garr, P, B, ptr(h["points"]), ptr(h["rotation"]),
+               ptr(h["translation"]), ptr(h["background"]), ptr(h["out_weight"]), ptr(h["point_weight"]), ptr(out)))
+    assert rel_l2(out, out_ref) <= TOL[dtype]
+    g = dict(points=np.empty((n_in, P), dtype, order="F"), rotation=np.empty((n_out, n_in, B), dtype, order="F"),
+             translation=np.empty((n_out, B), dtype, order="F"), background=np.empty(B, dtype), out_weight=np.empty(B, dtype),
+             point_weight=np.empty(P, dtype))
+    _lib.check(getattr(lib, f"dpr_raster_pullback_host_{suf}")(n_in, n_out, garr, P, B, ptr(h["ds_dout"]), ptr(h["points"]),
+               ptr(h["rotation"]), ptr(h["translation"]), ptr(h["out_weight"]), ptr(h["point_weight"]), ptr(g["points"]),
+               ptr(g["rotation"]), ptr(g["translation"]), ptr(g["background"]), ptr(g["out_weight"]), ptr(g["point_weight"])))
+    for k in FIELDS:
+        assert rel_l2(g[k], getattr(pb_ref, k)) <= TOL[dtype], k
+    lib.dpr_host_release()
