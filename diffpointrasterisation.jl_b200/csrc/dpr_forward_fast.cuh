@@ -191,7 +191,10 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                 if (HAS_PW) pwn = __ldg(point_weight + p0);
             }
         }
-        for (int it = 0; it < n_iter; ++it) {
+        for (int it0 = 0; it0 < n_iter; it0 += 64) {      // the 32-bit mass partial is folded into 64 bits every 64 chunks
+        const int it1 = (it0 + 64 < n_iter) ? it0 + 64 : n_iter;
+#pragma unroll 2
+        for (int it = it0; it < it1; ++it) {
             const int c = chunk_of(it);
             const int c0 = p_begin + c * kChunk;
             const bool active = c0 + (int)threadIdx.x < p_end;
@@ -250,10 +253,10 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                     __syncwarp();
                 }
             }
-            if ((it & 63) == 63) { mass += mass32; mass32 = 0; }
         }
         mass += mass32;
         mass32 = 0;
+        }
         if constexpr (CULL) __syncthreads();     // the chunk list is rebuilt in the next round
         }
         if (lane < wq_count) slow_point(wq[lane]);

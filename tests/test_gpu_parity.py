@@ -383,7 +383,8 @@ def test_baseline_configs_scaled(name, n_in, n_out, P, B, grid, dtype, weights):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("n_in,n_out,grid,B", [(3, 2, (64, 64), 300), (2, 2, (48, 32), 17), (3, 3, (16, 16, 16), 40)])
+@pytest.mark.parametrize("n_in,n_out,grid,B", [(3, 2, (64, 64), 300), (2, 2, (48, 32), 17), (3, 3, (16, 16, 16), 40),
+                                               (3, 2, (256, 256), 600)])   # 600 x 256 KB images: several 64 MB chunks
 def test_host_buffer_entry_points(dtype, n_in, n_out, grid, B):
     """dpr_raster_*_host_*: same results from HOST buffers (pose chunks pipelined over three streams through the
     library's staging arena), including the pose-sum of d_points across chunks."""
