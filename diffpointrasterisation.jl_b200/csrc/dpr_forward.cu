@@ -535,7 +535,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     const int64_t n_runs = (a.P + kChunk - 1) / kChunk;
     const size_t aabb_bytes = sizeof(float) * 2 * N_IN * (size_t)n_runs;
     if (tp.slabs >= 2 && tuning().point_sort != 2 && a.workspace && a.workspace_bytes >= sp.total + aabb_bytes && a.B >= 2) {
-        int rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+        int rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream, /*spread=*/true);
         if (rc != DPR_OK) return rc;
         char* ws = static_cast<char*>(a.workspace);
         pts = reinterpret_cast<const float*>(ws + sp.off_points);

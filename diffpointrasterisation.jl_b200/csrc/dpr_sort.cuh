@@ -135,14 +135,21 @@ static __global__ void __launch_bounds__(1024) bin_scan_kernel(uint32_t* __restr
     }
 }
 
+// `spread`: scatter forward-pass style - inside every full run of 1024 sorted points the order is permuted with a
+// stride permutation (i -> 33 i mod 1024), so the 32 lanes of a warp hold points that are ~32 apart in the sorted
+// order: the run stays spatially compact (culling, bounding boxes) but neighbouring lanes no longer hit the same cell
+// with their shared-memory atomics.
 template <typename T, int N_IN>
 __global__ void __launch_bounds__(256) bin_scatter_kernel(const T* __restrict__ points, const T* __restrict__ point_weight,
                                                           int64_t P, const uint32_t* __restrict__ keys,
                                                           uint32_t* __restrict__ offsets, int32_t* __restrict__ perm,
-                                                          T* __restrict__ sorted_points, T* __restrict__ sorted_pw) {
+                                                          T* __restrict__ sorted_points, T* __restrict__ sorted_pw,
+                                                          int spread) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint32_t full_runs_end = (uint32_t)(P & ~(int64_t)1023);
     for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
-        const uint32_t pos = atomicAdd(offsets + keys[p], 1u);
+        uint32_t pos = atomicAdd(offsets + keys[p], 1u);
+        if (spread && pos < full_runs_end) pos = (pos & ~1023u) | (((pos & 1023u) * 33u) & 1023u);
         perm[pos] = (int32_t)p;
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) sorted_points[(int64_t)pos * N_IN + j] = __ldg(points + p * N_IN + j);
@@ -218,7 +225,7 @@ inline SortPlan make_sort_plan(int n_in, int64_t P, int sizeof_T, bool has_pw, s
 
 template <typename T, int N_IN>
 static int sort_points(const T* points, const T* point_weight, int64_t P, void* workspace, const SortPlan& sp,
-                       const DeviceInfo& dev, cudaStream_t stream) {
+                       const DeviceInfo& dev, cudaStream_t stream, bool spread = false) {
     char* ws = static_cast<char*>(workspace);
     uint32_t* keys = reinterpret_cast<uint32_t*>(ws + sp.off_keys);
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + sp.off_counts);
@@ -238,7 +245,8 @@ static int sort_points(const T* points, const T* point_weight, int64_t P, void* 
     }
     {
         LaunchScope scope("bin_scatter", stream);
-        bin_scatter_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(points, point_weight, P, keys, counts, perm, spts, spw);
+        bin_scatter_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(points, point_weight, P, keys, counts, perm, spts, spw,
+                                                                          spread ? 1 : 0);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
