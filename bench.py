@@ -220,6 +220,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        # one process per GPU: run on the CPUs next to this GPU so the pinned host buffers of the end-to-end leg are
+        # first-touched on the local NUMA node (8 ranks otherwise fight over one socket's memory and inter-socket links)
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        except Exception:
+            pass
         dist.init_process_group("nccl", device_id=dev)
     td = torch.float32 if cfg["dtype"] == "f32" else torch.float64
     seed = 1000 + int(args.config[-1]) + (100 if args.config.startswith("readme") else 0)
