@@ -412,3 +412,43 @@ def test_host_buffer_entry_points(dtype, n_in, n_out, grid, B):
     for k in FIELDS:
         assert rel_l2(g[k], getattr(pb_ref, k)) <= TOL[dtype], k
     lib.dpr_host_release()
+
+
+def test_randomised_shapes_and_misaligned_buffers():
+    """Random small problems: odd grid extents, odd P and B, every dimension pair, both element types, inputs and
+    outputs that are trailing-axis slices of larger buffers (base pointers only element-aligned), all kernel paths."""
+    rng = np.random.default_rng(20261018)
+    dims = [(1, 1), (2, 1), (3, 1), (2, 2), (3, 2), (3, 3)]
+    for trial in range(36):
+        n_in, n_out = dims[trial % len(dims)]
+        dtype = np.float32 if (trial // len(dims)) % 2 == 0 else np.float64
+        td = torch.float32 if dtype == np.float32 else torch.float64
+        grid = tuple(int(rng.integers(3, 40 if n_out < 3 else 14)) for _ in range(n_out))
+        P, B = int(rng.integers(1, 3000)), int(rng.integers(1, 40))
+        weights = bool(trial % 3)
+        d = make_inputs(9000 + trial, n_in, n_out, P, B, grid, dtype, weights)
+        out_ref, pb_ref = _oracle_pair(d, grid, dtype)
+        # embed every array in a larger one and slice along the trailing axis: pointer offset = odd element count
+        def sliced(a):
+            if a is None:
+                return None
+            pad = np.zeros(a.shape[:-1] + (3,), dtype=a.dtype)
+            big = to_dev(np.concatenate([pad[..., :1], a, pad[..., :2]], axis=-1), td)
+            return big[..., 1:1 + a.shape[-1]]
+        args = tuple(sliced(d[k]) for k in ("points", "rotation", "translation", "background", "out_weight", "point_weight"))
+        ds = sliced(d["ds_dout"])
+        falgos = (0, 1, 2) if n_out == 2 else (0,)
+        for fa in falgos:
+            big_out = dpr_b200.empty_f(tuple(grid) + (B + 2,), td, "cuda")
+            out = big_out[..., 1:B + 1]
+            with forced(forward_algo=fa):
+                dpr_b200.raster_(out, *args)
+            assert rel_l2(to_np(out), out_ref) <= TOL[dtype], (trial, "fwd", fa, grid, P, B)
+        palgos = (0, 1, 2, 3) if n_out == 2 else (0, 1)
+        if n_out == 2 and dtype == np.float32 and (grid[0] * grid[1]) % 4 == 0:
+            palgos += (4,)
+        for pa in palgos:
+            with forced(pullback_algo=pa):
+                pb = dpr_b200.raster_pullback_(ds, *args)
+            for k in FIELDS:
+                assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (trial, "pullback", pa, k, grid, P, B)
