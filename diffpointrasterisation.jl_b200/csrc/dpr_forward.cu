@@ -417,9 +417,10 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
     const int64_t g0 = a.grid[0], g1 = a.grid[1];
     int64_t budget = tuning().tile_smem_bytes > 0 ? tuning().tile_smem_bytes : (int64_t)dev.max_smem_optin - 1024;
     if (budget > (int64_t)dev.max_smem_optin - 1024) budget = (int64_t)dev.max_smem_optin - 1024;
-    // Float32 with 16-byte aligned inputs takes the TMA-staged fixed-point kernel, which needs staging space
-    use_fast = sizeof(T) == 4 && tuning().forward_accum != 1 && (reinterpret_cast<uintptr_t>(a.points) & 15) == 0 &&
-               (!a.point_weight || ((reinterpret_cast<uintptr_t>(a.point_weight) & 15) == 0 && a.workspace && a.workspace_bytes >= 16));
+    // Float32 takes the fixed-point kernel (dpr_forward_fast.cuh), which needs room for its per-warp queues and, with
+    // point weights, 256 bytes of workspace for their statistics
+    use_fast = sizeof(T) == 4 && tuning().forward_accum != 1 &&
+               (!a.point_weight || (a.workspace && a.workspace_bytes >= 256));
     int64_t extra = use_fast ? (int64_t)fast_extra_smem(false) + 128 : 0;
     const int64_t extra_cull = use_fast ? (int64_t)fast_extra_smem(true) - (int64_t)fast_extra_smem(false) : 0;
     if (use_fast && tuning().tile_smem_bytes == 0) budget -= extra;
