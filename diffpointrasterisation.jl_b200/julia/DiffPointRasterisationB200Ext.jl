@@ -103,11 +103,47 @@ function DiffPointRasterisation.raster!(
 end
 
 # --------------------------------------------------------------------------------------------------------------
-# pullback, single image: the reference's extension only defines an error stub for it
-# (ext/DiffPointRasterisationCUDAExt.jl:213-228).  libdpr handles B = 1 with the batch kernels, so a single-image
-# method can forward to the batch method with a singleton batch dimension; that method is SURVEY.md 8f-3 ("next")
-# and is deliberately not defined here yet, which leaves the reference behaviour (CPU-array path / error) in place.
+# pullback, single image: the reference's extension only has an error stub for it
+# (ext/DiffPointRasterisationCUDAExt.jl:213-228).  libdpr handles B = 1 with the batch kernels (the points are split
+# over the SMs), so the single-image method forwards to the batch method with a singleton batch dimension and
+# unwraps the per-pose results, returning the same NamedTuple as the CPU method (src/raster_pullback.jl:74-81).
 # --------------------------------------------------------------------------------------------------------------
+function DiffPointRasterisation.raster_pullback!(
+    ds_dout::CuArray{T,N_out},
+    points::CuVector{<:StaticVector{N_in,T}},
+    rotation::StaticMatrix{N_out,N_in,T},
+    translation::StaticVector{N_out,T},
+    background::Number,
+    out_weight::Number,
+    point_weight::CuOrFillVector{T},
+    ds_dpoints::CuMatrix{T},
+    ds_dpoint_weight::CuVector{T};
+    kwargs...,
+) where {T<:Union{Float32,Float64},N_in,N_out}
+    res = DiffPointRasterisation.raster_pullback!(
+        reshape(ds_dout, size(ds_dout)..., 1),
+        points,
+        CuArray([SMatrix{N_out,N_in,T}(rotation)]),
+        CuArray([SVector{N_out,T}(translation)]),
+        Zeros(T, 1),                    # background does not enter the gradients
+        CUDA.fill(T(out_weight), 1),
+        point_weight,
+        ds_dpoints,
+        CuArray{T}(undef, N_out, N_in, 1),
+        CuArray{T}(undef, N_out, 1),
+        CuArray{T}(undef, 1),
+        CuArray{T}(undef, 1),
+        ds_dpoint_weight,
+    )
+    return (;
+        points=res.points,
+        rotation=SMatrix{N_out,N_in,T}(Array(res.rotation)[:, :, 1]),
+        translation=SVector{N_out,T}(Array(res.translation)[:, 1]),
+        background=Array(res.background)[1],
+        out_weight=Array(res.out_weight)[1],
+        point_weight=res.point_weight,
+    )
+end
 
 # --------------------------------------------------------------------------------------------------------------
 # pullback, batch of images: same 13-argument signature as ext/DiffPointRasterisationCUDAExt.jl:231-245
