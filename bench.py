@@ -198,7 +198,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--cpu-poses", type=int, default=1024, help="poses in the cpu_baseline sample")
+    ap.add_argument("--cpu-poses", type=int, default=2048, help="poses in the cpu_baseline sample")
     ap.add_argument("--ref-poses", type=int, default=512, help="poses per step of the --impl reference arm")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
