@@ -133,21 +133,21 @@ struct TileParams {
     int band_lo, band_hi;  // rows covered by shared-memory slabs
     int exclusive;    // 1: CTA owns its cells -> flush = store(tile + bg) and it initialises border rows itself
                       // 0: out was pre-filled with the background -> flush = REDG
-    int fixed_bits;   // F > 0: try the fixed-point mode with F fractional bits; 0: float CAS only
-    const float* pw_stats;  // device: {max, min, mean} of point_weight (fixed-point eligibility), or NULL
+    int fixed_bits;   // planning only: fractional bits F for the Float32 fixed-point kernel (dpr_forward_fast.cuh)
 };
 
 constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it leaves rint(x) in the low mantissa bits
 constexpr int kMagicBits = 0x4B400000;
 
-template <typename T, int N_IN, bool FIXED>
-__device__ __forceinline__ long long tile_accumulate(T* __restrict__ tile, T* __restrict__ img, const T* __restrict__ points,
-                                                     const T* __restrict__ point_weight, const Pose<T, N_IN, 2>& pose,
-                                                     const Grid<T, 2>& grid, int p_begin, int p_end, int ys, int ye,
-                                                     int band_lo, int band_hi, bool do_border, float qscale) {
+// Generic slab accumulation with shared-memory atomicAdd in the element type (CAS loop on sm_100a): used for Float64
+// and as the fallback of the Float32 fixed-point kernel.
+template <typename T, int N_IN>
+__device__ __forceinline__ void tile_accumulate(T* __restrict__ tile, T* __restrict__ img, const T* __restrict__ points,
+                                                const T* __restrict__ point_weight, const Pose<T, N_IN, 2>& pose,
+                                                const Grid<T, 2>& grid, int p_begin, int p_end, int ys, int ye,
+                                                int band_lo, int band_hi, bool do_border) {
     const int g0 = grid.g[0], g1 = grid.g[1];
     const int nrows = ye - ys;
-    long long mass = 0;
     int p = p_begin + threadIdx.x;
     T xn[N_IN], pwn = T(1);
     if (p < p_end) {
@@ -173,15 +173,7 @@ __device__ __forceinline__ long long tile_accumulate(T* __restrict__ tile, T* __
         const T v00 = (du0 * du1) * weight, v10 = (dl[0] * du1) * weight;   // src/raster.jl:63, 104-106
         const T v01 = (du0 * dl[1]) * weight, v11 = (dl[0] * dl[1]) * weight;
         const int ry = i0[1] - ys;
-        auto tile_add = [&](int off, T v) {
-            if constexpr (FIXED) {
-                const int q = __float_as_int(fmaf((float)v, qscale, kMagic)) - kMagicBits;
-                atomicAdd(reinterpret_cast<int*>(tile) + off, q);
-                mass += q;
-            } else {
-                atomicAdd(tile + off, v);
-            }
-        };
+        auto tile_add = [&](int off, T v) { atomicAdd(tile + off, v); };
         if ((unsigned)i0[0] < (unsigned)(g0 - 1) && (unsigned)ry < (unsigned)(nrows - 1)) {
             // interior of the slab: all four corners are in bounds and on chip
             const int off = ry * g0 + i0[0];
@@ -209,7 +201,6 @@ __device__ __forceinline__ long long tile_accumulate(T* __restrict__ tile, T* __
             }
         }
     }
-    return mass;
 }
 
 __device__ __forceinline__ long long block_sum_ll(long long v, long long* scratch) {
@@ -261,8 +252,8 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
     }
     __syncthreads();
 
-    tile_accumulate<T, N_IN, false>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
-                                    tp.band_hi, do_border, 0.f);
+    tile_accumulate<T, N_IN>(tile, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo, tp.band_hi,
+                             do_border);
     __syncthreads();
 
     auto cell_value = [&](int i) -> T { return tile[i]; };
@@ -463,7 +454,6 @@ static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TilePara
     tp.exclusive = (Q == 1) ? 1 : 0;
     // fixed-point fractional bits: headroom for ~64x the mean number of points per cell before a 32-bit cell wraps
     tp.fixed_bits = 0;
-    tp.pw_stats = nullptr;
     if (use_fast) {
         const double per_cell = (double)a.P / (double)(g0 * g1);
         int head = 6;
@@ -482,8 +472,7 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
         int rc = launch_fill_background(a.out, a.background, grid.cells, a.B, dev, a.stream);
         if (rc != DPR_OK) return rc;
     }
-    TileParams<T> tpl = tp;
-    tpl.fixed_bits = 0;
+    const TileParams<T>& tpl = tp;
     auto kern = fwd_splat_tile2d_kernel<T, N_IN>;
     DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
     const int64_t ctas = a.B * tp.slabs * tp.splits;

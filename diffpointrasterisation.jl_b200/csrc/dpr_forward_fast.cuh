@@ -271,13 +271,13 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
             fixed = false;
             for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile_f[i] = 0.f;
             __syncthreads();
-            tile_accumulate<float, N_IN, false>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
-                                                tp.band_lo, tp.band_hi, false, 0.f);
+            tile_accumulate<float, N_IN>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
+                                         tp.band_hi, false);
             __syncthreads();
         }
     } else {
-        tile_accumulate<float, N_IN, false>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye,
-                                            tp.band_lo, tp.band_hi, do_border, 0.f);
+        tile_accumulate<float, N_IN>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
+                                     tp.band_hi, do_border);
         __syncthreads();
     }
 
