@@ -546,8 +546,9 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
         return DPR_OK;
     };
     int rc;
-    if (fp.aabb) rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, true>) : launch(fwd_tile2d_fast_kernel<N_IN, false, true>);
-    else rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, false>) : launch(fwd_tile2d_fast_kernel<N_IN, false, false>);
+    if (fp.aabb) rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, 2>) : launch(fwd_tile2d_fast_kernel<N_IN, false, 2>);
+    else if (tp.slabs > 1) rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, 1>) : launch(fwd_tile2d_fast_kernel<N_IN, false, 1>);
+    else rc = has_pw ? launch(fwd_tile2d_fast_kernel<N_IN, true, 0>) : launch(fwd_tile2d_fast_kernel<N_IN, false, 0>);
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
     const bool border = tp.band_lo > 0 || tp.band_hi < (int)a.grid[1];

@@ -36,12 +36,15 @@ __host__ __device__ inline size_t fast_extra_smem(bool cull) {
     return (size_t)32 * kQueueCap * 4 + (cull ? (size_t)kChunk * 4 : 0);
 }
 
-template <int N_IN, bool HAS_PW, bool CULL>
+// MODE 0: one slab per pose (whole image, hybrid band, or point splits); 1: several slabs; 2: several slabs with
+// spatially sorted points and per-run culling.
+template <int N_IN, bool HAS_PW, int MODE>
 __global__ void __launch_bounds__(1024, 1)
 fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict__ rotation,
                        const float* __restrict__ translation, const float* __restrict__ background,
                        const float* __restrict__ out_weight, const float* __restrict__ point_weight,
                        float* __restrict__ out, Grid<float, 2> grid, int P, FastTileParams tp) {
+    constexpr bool CULL = MODE == 2;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ long long scratch[32];
     const int per_pose = tp.slabs * tp.splits;
@@ -239,9 +242,13 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                 tile_add(off + g0 + 1, dl.x * bq);
             }
             // ---- defer the lanes that are not interior but touch this CTA's cells (warp-level compaction) ------
-            const bool touches_slab = (unsigned)(ry + 1) < (unsigned)(nrows + 1);
-            const bool touches_border = do_border && (iy < tp.band_lo || iy + 1 >= tp.band_hi);
-            const bool slow = active && !interior && (touches_slab || touches_border);
+            bool slow = active && !interior;
+            if constexpr (MODE != 0) {
+                // several slabs: a point of another slab is not this CTA's business (there are no border rows then)
+                slow = slow && (unsigned)(ry + 1) < (unsigned)(nrows + 1);
+            }
+            // MODE 0: every non-interior point either straddles the slab edge, lies in the border rows handled with
+            // REDG by this CTA, or is (partly) outside the image: slow_point sorts that out
             const unsigned slow_mask = __ballot_sync(0xffffffffu, slow);
             if (slow_mask) {
                 if (slow) wq[wq_count + __popc(slow_mask & ((1u << lane) - 1u))] = c0 + (int)threadIdx.x;
