@@ -4,7 +4,7 @@ The product is the CUDA library `libdpr.so` (csrc/, C ABI in include/dpr.h).  Th
 mirror of the reference's interface used by the tests and the benchmark; Julia binds the same symbols with `ccall`
 (see INTEGRATION.md and julia/).
 """
-from . import _lib, build  # noqa: F401
+from . import _lib, autograd, build  # noqa: F401
 from ._lib import DprError, kernel_launch_count, last_path, set_option, get_option  # noqa: F401
 from .interface import (DimensionMismatch, PullbackResult, empty_f, fortran, is_fortran, raster, raster_,  # noqa: F401
                         raster_pullback_)

@@ -452,3 +452,45 @@ def test_randomised_shapes_and_misaligned_buffers():
                 pb = dpr_b200.raster_pullback_(ds, *args)
             for k in FIELDS:
                 assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (trial, "pullback", pa, k, grid, P, B)
+
+
+@pytest.mark.parametrize("n_out,grid", [(3, (8, 8, 8)), (2, (8, 8))])
+@pytest.mark.parametrize("optional", [True, False])
+@pytest.mark.parametrize("single", [False, True])
+def test_rrule_finite_differences(n_out, grid, optional, single):
+    """The reference's ChainRules tests (test/chainrules.jl:2-90: test_rrule on 3->3 and 3->2, with and without the
+    optional arguments, single image and batch; fixtures of test/data.jl: 10 points, 8^n grid) re-expressed:
+    the reverse rule built from raster + raster_pullback! (dpr_b200.autograd.raster, mirror of
+    ext/DiffPointRasterisationChainRulesCoreExt.jl:48-74) against central finite differences of the CUDA forward."""
+    from dpr_b200 import autograd
+    B = 1 if single else 5
+    d = make_inputs(17 + n_out, 3, n_out, 10, B, grid, np.float64, True)
+    names = ["points", "rotation", "translation"] + (["background", "out_weight", "point_weight"] if optional else [])
+    vals = {k: d[k] for k in names}
+    if single:
+        vals["rotation"], vals["translation"] = d["rotation"][..., 0], d["translation"][..., 0]
+        if optional:
+            vals["background"], vals["out_weight"] = d["background"][:1].reshape(()), d["out_weight"][:1].reshape(())
+    w = d["ds_dout"][..., 0] if single else d["ds_dout"]
+    w_dev = to_dev(w)
+    tens = {k: to_dev(np.asarray(v)).requires_grad_(True) for k, v in vals.items()}
+    out = autograd.raster(grid, *[tens[k] for k in names])
+    (out * w_dev).sum().backward()
+
+    def loss(vv):
+        with torch.no_grad():
+            o = dpr_b200.raster(grid, *[to_dev(np.asarray(vv[k])) for k in names])
+        return float((o * w_dev).sum())
+
+    rng = np.random.default_rng(3)
+    eps = 1e-7
+    for k in names:
+        direction = rng.standard_normal(np.shape(vals[k]))
+        plus, minus = dict(vals), dict(vals)
+        plus[k] = np.asarray(vals[k]) + eps * direction
+        minus[k] = np.asarray(vals[k]) - eps * direction
+        fd = (loss(plus) - loss(minus)) / (2 * eps)
+        an = float((tens[k].grad.cpu().numpy() * direction).sum())
+        assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (k, fd, an)
+    if not optional:   # no tangent for arguments that were not passed (ext/...ChainRulesCoreExt.jl:68-70)
+        assert set(tens) == {"points", "rotation", "translation"}
