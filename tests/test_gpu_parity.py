@@ -494,3 +494,23 @@ def test_rrule_finite_differences(n_out, grid, optional, single):
         assert abs(fd - an) <= 1e-5 * max(1.0, abs(an)), (k, fd, an)
     if not optional:   # no tangent for arguments that were not passed (ext/...ChainRulesCoreExt.jl:68-70)
         assert set(tens) == {"points", "rotation", "translation"}
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n_out,grid", [(2, (24, 16)), (3, (8, 8, 8))])
+def test_default_arguments_equal_explicit(dtype, n_out, grid):
+    """src/interface.jl:485-504, :575-594: leaving out background / out_weight / point_weight is the same as passing
+    zeros / ones / ones (FillArrays defaults, src/interface.jl:368-394 -> NULL pointers here)."""
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    d = make_inputs(64, 3, n_out, 3000, 5, grid, dtype, False)
+    pts, rot, tr = (to_dev(d[k], td) for k in ("points", "rotation", "translation"))
+    zeros, ones_b, ones_p = torch.zeros(5, dtype=td, device="cuda"), torch.ones(5, dtype=td, device="cuda"), torch.ones(3000, dtype=td, device="cuda")
+    ds = to_dev(d["ds_dout"], td)
+    combos = [(), (zeros,), (zeros, ones_b), (zeros, ones_b, ones_p)]
+    outs = [dpr_b200.raster(grid, pts, rot, tr, *c) for c in combos]
+    pbs = [dpr_b200.raster_pullback_(ds, pts, rot, tr, *c) for c in combos]
+    for o in outs[1:]:
+        assert rel_l2(to_np(o), to_np(outs[0])) <= (1e-6 if dtype == np.float32 else 1e-13)
+    for pb in pbs[1:]:
+        for k in FIELDS:
+            assert rel_l2(to_np(getattr(pb, k)), to_np(getattr(pbs[0], k))) <= (1e-5 if dtype == np.float32 else 1e-12), k
