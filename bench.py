@@ -99,6 +99,9 @@ class ClockSampler(threading.Thread):
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
             self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            # first NVML queries are slow: make them before the timed region
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            pynvml.nvmlDeviceGetCurrentClocksEventReasons(self.h)
         except Exception:
             self.nv = None
 
@@ -381,7 +384,7 @@ def main():
         threads = host_threads()
         n_poses = min(B, args.cpu_poses)
         cpu_port_time(cfg, inputs, min(n_poses, threads), threads)  # warm the threads
-        tf, tb = cpu_port_time(cfg, inputs, n_poses, threads)
+        tf, tb = min((cpu_port_time(cfg, inputs, n_poses, threads) for _ in range(2)), key=sum)   # best of two passes
         cpu_baseline = dict(value=P * n_poses / (tf + tb), unit=UNIT, cores=threads, kind="port",
                             sample=f"first {n_poses} of {B} poses, all {P} points, one pass (fwd {tf:.2f}s + bwd {tb:.2f}s)",
                             fwd_splats_per_s=(P * n_poses / tf) if tf else None, bwd_splats_per_s=P * n_poses / tb)
