@@ -514,3 +514,24 @@ def test_default_arguments_equal_explicit(dtype, n_out, grid):
     for pb in pbs[1:]:
         for k in FIELDS:
             assert rel_l2(to_np(getattr(pb, k)), to_np(getattr(pbs[0], k))) <= (1e-5 if dtype == np.float32 else 1e-12), k
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("grid", [(1, 1), (1, 37), (64, 1), (2, 2), (3, 500), (1024, 4), (1, 1, 9), (2, 1, 2)])
+def test_degenerate_grids(dtype, grid):
+    """One-cell-wide grids and extreme aspect ratios: no interior exists, everything goes through the edge paths."""
+    n_out = len(grid)
+    d = make_inputs(777, 3, n_out, 4000, 7, grid, dtype)
+    out_ref, pb_ref = _oracle_pair(d, grid, dtype)
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    args = dev_args(d, dtype)
+    for fa in ((0, 1, 2) if n_out == 2 else (0,)):
+        with forced(forward_algo=fa):
+            out = dpr_b200.raster(grid, *args)
+        assert rel_l2(to_np(out), out_ref) <= TOL[dtype], (grid, fa, dpr_b200.last_path(0))
+    palgos = (0, 1, 2, 3) + ((4,) if (dtype == np.float32 and n_out == 2 and (grid[0] * grid[1]) % 4 == 0) else ()) if n_out == 2 else (0, 1)
+    for pa in palgos:
+        with forced(pullback_algo=pa):
+            pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], td), *args)
+        for k in FIELDS:
+            assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (grid, pa, k, dpr_b200.last_path(1))
