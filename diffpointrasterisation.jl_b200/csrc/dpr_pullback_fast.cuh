@@ -42,7 +42,6 @@ __device__ __forceinline__ void butterfly8(T (&a)[8], int lane) {
 }
 
 // lower-corner cell (0-based) and dl for the 2-d case, bit-identical to dpr_common.cuh::stencil.
-// Non-finite or far-away coordinates give indices for which every corner predicate below is false.
 template <typename T, int N_IN>
 __device__ __forceinline__ void stencil2(const T (&x)[N_IN], const T (&R)[2][N_IN], const T (&neg_origin)[2],
                                          const T (&scale)[2], const int (&g)[2], int& ix, int& iy, T (&dl)[2]) {
@@ -72,10 +71,12 @@ __device__ __forceinline__ void stencil2(const T (&x)[N_IN], const T (&R)[2][N_I
             dl[k] = sub_rn(coord, sub_rn(r[k], T(0.5)));
         }
     }
-    // clamp in floating point first: NaN -> -2, huge -> g+2, so the integer conversion is always safe
-    const T rx = fmin(fmax(r[0], T(-2)), T(g[0] + 2)), ry = fmin(fmax(r[1], T(-2)), T(g[1] + 2));
-    ix = to_int_sat(rx) - 1;
-    iy = to_int_sat(ry) - 1;
+    // cvt.rni.s32 saturates (huge -> INT_MAX / INT_MIN, NaN -> 0), and the -1 is done modulo 2^32, so far-away points
+    // end up with indices for which every corner predicate of the callers is false; a NaN coordinate maps to
+    // index -1 (one in-bounds column, memory-safe) and its NaN weights propagate to the results.
+    (void)g;
+    ix = (int)((unsigned)to_int_sat(r[0]) - 1u);
+    iy = (int)((unsigned)to_int_sat(r[1]) - 1u);
 }
 
 template <typename T, int N_IN, int K, bool HAS_PW, bool PAIR>
