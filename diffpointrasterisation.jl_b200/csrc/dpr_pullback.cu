@@ -239,12 +239,10 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
         grid.scale[k] = T(a.grid[k]) / T(2);  // src/raster_pullback.jl:29
         grid.cells *= a.grid[k];
     }
-    // zero everything that is accumulated with REDG (ext/DiffPointRasterisationCUDAExt.jl:272-276)
-    DPR_CUDA_TRY(cudaMemsetAsync(a.d_points, 0, sizeof(T) * (size_t)(a.P * N_IN), a.stream));
-    DPR_CUDA_TRY(cudaMemsetAsync(a.d_rotation, 0, sizeof(T) * (size_t)(a.B * N_OUT * N_IN), a.stream));
-    DPR_CUDA_TRY(cudaMemsetAsync(a.d_translation, 0, sizeof(T) * (size_t)(a.B * N_OUT), a.stream));
-    if (a.d_out_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_out_weight, 0, sizeof(T) * (size_t)a.B, a.stream));
-    if (a.d_point_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_point_weight, 0, sizeof(T) * (size_t)a.P, a.stream));
+    {
+        int rcz = zero_gradients(a);
+        if (rcz != DPR_OK) return rcz;
+    }
     int rc = launch_background_sum(a, grid.cells, dev);
     if (rc != DPR_OK) return rc;
     if (a.P == 0 || a.B == 0) return DPR_OK;
@@ -294,15 +292,42 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 #include "dpr_pullback_tma.cuh"
 namespace dpr {
 
-// zero everything that is accumulated with REDG (ext/DiffPointRasterisationCUDAExt.jl:272-276)
+// zero everything that is accumulated with REDG (the five fill! calls of ext/DiffPointRasterisationCUDAExt.jl:272-276)
+// in ONE launch: for small problems the step is launch bound, five memsets are five launches
+struct ZeroList {
+    void* ptr[5];
+    unsigned long long bytes[5];   // each a multiple of 4
+};
+__global__ void __launch_bounds__(256) zero_buffers_kernel(ZeroList z) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        uint32_t* p = static_cast<uint32_t*>(z.ptr[k]);
+        const size_t n = (size_t)(z.bytes[k] / 4);
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0u;
+    }
+}
+
 template <typename T>
 static int zero_gradients(const PullbackArgs<T>& a) {
     const int nr = a.n_in * a.n_out;
-    DPR_CUDA_TRY(cudaMemsetAsync(a.d_points, 0, sizeof(T) * (size_t)(a.P * a.n_in), a.stream));
-    DPR_CUDA_TRY(cudaMemsetAsync(a.d_rotation, 0, sizeof(T) * (size_t)(a.B * nr), a.stream));
-    DPR_CUDA_TRY(cudaMemsetAsync(a.d_translation, 0, sizeof(T) * (size_t)(a.B * a.n_out), a.stream));
-    if (a.d_out_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_out_weight, 0, sizeof(T) * (size_t)a.B, a.stream));
-    if (a.d_point_weight) DPR_CUDA_TRY(cudaMemsetAsync(a.d_point_weight, 0, sizeof(T) * (size_t)a.P, a.stream));
+    ZeroList z;
+    z.ptr[0] = a.d_points;       z.bytes[0] = sizeof(T) * (unsigned long long)(a.P * a.n_in);
+    z.ptr[1] = a.d_rotation;     z.bytes[1] = sizeof(T) * (unsigned long long)(a.B * nr);
+    z.ptr[2] = a.d_translation;  z.bytes[2] = sizeof(T) * (unsigned long long)(a.B * a.n_out);
+    z.ptr[3] = a.d_out_weight;   z.bytes[3] = a.d_out_weight ? sizeof(T) * (unsigned long long)a.B : 0;
+    z.ptr[4] = a.d_point_weight; z.bytes[4] = a.d_point_weight ? sizeof(T) * (unsigned long long)a.P : 0;
+    unsigned long long most = 0;
+    for (int k = 0; k < 5; ++k) most = z.bytes[k] > most ? z.bytes[k] : most;
+    if (most == 0) return DPR_OK;
+    unsigned long long blocks = (most / 4 + 255) / 256;
+    if (blocks > 592) blocks = 592;
+    if (blocks < 1) blocks = 1;
+    {
+        LaunchScope scope("zero_gradients", a.stream);
+        zero_buffers_kernel<<<(unsigned)blocks, 256, 0, a.stream>>>(z);
+    }
+    DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
 }
 
