@@ -487,7 +487,7 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
     return DPR_OK;
 }
 
-// Float32 fast path: TMA-staged points, packed FP32x2 stencil, fixed-point native shared-memory atomics
+// Float32 fast path: packed FP32x2 stencil, fixed-point native shared-memory atomics, optional run culling
 template <int N_IN>
 static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& dev, const TileParams<float>& tp, size_t smem_bytes) {
     const Grid<float, 2> grid = make_grid<float, 2>(a.grid);

@@ -6,10 +6,10 @@
 //   * the next chunk's point is prefetched into registers while the current one is processed (a TMA-staged variant,
 //     cp.async.bulk per 1024-point chunk behind a full/empty mbarrier pair, measured SLOWER - 3.03 ms vs 2.03 ms on
 //     config 2 - because one shared stage forces the 32 warps into lock-step and exposes the copy latency, while a
-//     second stage costs 12 rows of tile; the mbarrier/TMA helpers below are kept for the pullback's image staging);
-//   * the transform and the stencil run on Blackwell's packed FP32x2 pipe (FMUL2/FADD2/FFMA2: both output
-//     dimensions in one instruction), still unfused and in the reference's operation order, so cell assignment is
-//     bit-identical to the scalar path (dpr_common.cuh::stencil);
+//     second stage costs 12 rows of tile; TMA is used where it fits: dpr_pullback_tma.cuh stages whole pose images);
+//   * the transform and the stencil run on Blackwell's packed FP32x2 pipe (FMUL2/FADD2: both output dimensions in
+//     one instruction), still unfused and in the reference's operation order, so cell assignment is bit-identical
+//     to the scalar path (dpr_common.cuh::stencil) - see the ptxas note at the stencil below;
 //   * accumulation is fixed-point on the native 32-bit ATOMS.ADD (see dpr_forward.cu header comment); a 64-bit mass
 //     checksum detects a wrapped cell exactly and the CTA then redoes the slab with float CAS atomics;
 //   * the ~5% of lanes whose stencil leaves the slab (image border, slab edge) are not handled inline - that made
@@ -19,7 +19,7 @@
 
 namespace dpr {
 
-constexpr int kChunk = 1024;          // points per TMA chunk = threads per CTA
+constexpr int kChunk = 1024;          // points per chunk = threads per CTA = length of a culling run
 constexpr int kQueueCap = 64;         // per-warp deferred-point queue (ints)
 
 struct FastTileParams {
