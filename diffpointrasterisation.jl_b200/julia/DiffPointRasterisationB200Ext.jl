@@ -25,9 +25,6 @@ const CuOrFillVector{T} = CuOrFillArray{T,1}
 const DPR_OP_FORWARD = Cint(0)
 const DPR_OP_PULLBACK = Cint(1)
 
-_suffix(::Type{Float32}) = "f32"
-_suffix(::Type{Float64}) = "f64"
-
 function _check(rc::Cint)
     rc == 0 && return nothing
     msg = unsafe_string(ccall((:dpr_status_string, libdpr), Cstring, (Cint,), rc))
@@ -37,15 +34,14 @@ end
 
 # FillArrays defaults (src/interface.jl:368-394) map to NULL: Zeros background, Ones weights.
 # Any other Fill value is materialised (rare; keeps the semantics of the reference).
+_null(::Type{T}) where {T} = reinterpret(CuPtr{T}, CUDA.CU_NULL)
 _devptr(::Type{T}, a::CuArray{T}) where {T} = pointer(a)
-_devptr(::Type{T}, a::FillArrays.Zeros{T}) where {T} = CU_NULL
-_devptr(::Type{T}, a::FillArrays.Ones{T}) where {T} = CU_NULL
+_devptr(::Type{T}, a::FillArrays.Zeros{T}) where {T} = _null(T)
+_devptr(::Type{T}, a::FillArrays.Ones{T}) where {T} = _null(T)
 _materialise(a::CuArray) = a
 _materialise(a::FillArrays.Zeros) = a
 _materialise(a::FillArrays.Ones) = a
 _materialise(a::FillArrays.AbstractFill{T}) where {T} = CUDA.fill(FillArrays.getindex_value(a), size(a)...)
-_is_default_zero(a) = a isa FillArrays.Zeros
-_is_default_one(a) = a isa FillArrays.Ones
 
 function _workspace(op, n_in, n_out, grid::Vector{Int64}, P, B, ::Type{T}) where {T}
     nbytes = ccall((:dpr_workspace_bytes, libdpr), Csize_t,
@@ -76,7 +72,6 @@ function DiffPointRasterisation.raster!(
     background, out_weight, point_weight = _materialise(background), _materialise(out_weight), _materialise(point_weight)
     grid = collect(Int64, size(out)[1:N_out])
     ws = _workspace(DPR_OP_FORWARD, N_in, N_out, grid, n_points, batch_size, T)
-    fn = T === Float32 ? :dpr_raster_forward_f32 : :dpr_raster_forward_f64
     GC.@preserve out points rotation translation background out_weight point_weight ws begin
         rc = if T === Float32
             ccall((:dpr_raster_forward_f32, libdpr), Cint,
