@@ -141,29 +141,25 @@ constexpr int kMagicBits = 0x4B400000;
 
 // Generic slab accumulation with shared-memory atomicAdd in the element type (CAS loop on sm_100a): used for Float64
 // and as the fallback of the Float32 fixed-point kernel.
-template <typename T, int N_IN>
-__device__ __forceinline__ void tile_accumulate(T* __restrict__ tile, T* __restrict__ img, const T* __restrict__ points,
-                                                const T* __restrict__ point_weight, const Pose<T, N_IN, 2>& pose,
-                                                const Grid<T, 2>& grid, int p_begin, int p_end, int ys, int ye,
-                                                int band_lo, int band_hi, bool do_border) {
+// `load(p, x, pw)` fetches point p and its weight (AoS arrays here, the packed float4 copy in dpr_forward_radial.cuh).
+template <typename T, int N_IN, typename Loader>
+__device__ __forceinline__ void tile_accumulate_with(T* __restrict__ tile, T* __restrict__ img, Loader load,
+                                                     const Pose<T, N_IN, 2>& pose, const Grid<T, 2>& grid, int p_begin,
+                                                     int p_end, int ys, int ye, int band_lo, int band_hi, bool do_border) {
     const int g0 = grid.g[0], g1 = grid.g[1];
     const int nrows = ye - ys;
     int p = p_begin + threadIdx.x;
     T xn[N_IN], pwn = T(1);
-    if (p < p_end) {
-        load_point(xn, points, p);
-        if (point_weight) pwn = __ldg(point_weight + p);
-    }
+#pragma unroll
+    for (int j = 0; j < N_IN; ++j) xn[j] = T(0);
+    if (p < p_end) load(p, xn, pwn);
     while (p < p_end) {
         T x[N_IN];
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) x[j] = xn[j];
         const T pw = pwn;
         const int pn = p + blockDim.x;
-        if (pn < p_end) {   // prefetch the next point while this one is processed
-            load_point(xn, points, pn);
-            if (point_weight) pwn = __ldg(point_weight + pn);
-        }
+        if (pn < p_end) load(pn, xn, pwn);   // prefetch the next point while this one is processed
         p = pn;
         int i0[2];
         T dl[2];
@@ -201,6 +197,18 @@ __device__ __forceinline__ void tile_accumulate(T* __restrict__ tile, T* __restr
             }
         }
     }
+}
+
+template <typename T, int N_IN>
+__device__ __forceinline__ void tile_accumulate(T* __restrict__ tile, T* __restrict__ img, const T* __restrict__ points,
+                                                const T* __restrict__ point_weight, const Pose<T, N_IN, 2>& pose,
+                                                const Grid<T, 2>& grid, int p_begin, int p_end, int ys, int ye,
+                                                int band_lo, int band_hi, bool do_border) {
+    auto load = [&](int p, T (&x)[N_IN], T& pw) {
+        load_point(x, points, (int64_t)p);
+        if (point_weight) pw = __ldg(point_weight + p);
+    };
+    tile_accumulate_with<T, N_IN>(tile, img, load, pose, grid, p_begin, p_end, ys, ye, band_lo, band_hi, do_border);
 }
 
 __device__ __forceinline__ long long block_sum_ll(long long v, long long* scratch) {
@@ -325,6 +333,7 @@ __global__ void __launch_bounds__(32) point_weight_stats_finish_kernel(const flo
 
 }  // namespace dpr
 #include "dpr_forward_fast.cuh"
+#include "dpr_forward_radial.cuh"
 namespace dpr {
 
 // ---------------------------------------------------------------------------------------------------------
@@ -517,6 +526,36 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
         }
         fp.pw_stats = stats;
     }
+    // One slab per pose and enough work to amortise a counting sort: radius-sorted points, straight-line loop for the
+    // chunks that are interior for a pose by Cauchy-Schwarz (dpr_forward_radial.cuh)
+    {
+        const RadialPlan rp = make_radial_plan(a.P, 256);
+        const int64_t ps = tuning().point_sort;
+        const bool want = ps == 1 || (ps == 0 && a.P >= 8192 && (double)a.P * (double)a.B >= 6.4e7);
+        if (tp.slabs == 1 && want && a.workspace && a.workspace_bytes >= rp.total && a.P < (int64_t)0x3ffffc00) {
+            int rc = radial_sort_points<N_IN>(a.points, a.point_weight, fp.pw_stats, a.P, a.workspace, rp, dev, a.stream);
+            if (rc != DPR_OK) return rc;
+            char* ws = static_cast<char*>(a.workspace);
+            const float4* pts4 = reinterpret_cast<const float4*>(ws + rp.off_pts4);
+            const float* rmax = reinterpret_cast<const float*>(ws + rp.off_rmax);
+            const int64_t chunks_per_split = (rp.n_chunks + tp.splits - 1) / tp.splits;
+            fp.per_split = (int)(chunks_per_split * kChunk);
+            const int64_t ctas = a.B * tp.splits;
+            auto launch = [&](auto kern) -> int {
+                DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+                LaunchScope scope("fwd_tile2d_radial", a.stream);
+                kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(pts4, rmax, a.rotation, a.translation, a.background,
+                                                                     a.out_weight, a.out, grid, rp.n_chunks, fp);
+                return DPR_OK;
+            };
+            rc = has_pw ? launch(fwd_tile2d_radial_kernel<N_IN, true>) : launch(fwd_tile2d_radial_kernel<N_IN, false>);
+            if (rc != DPR_OK) return rc;
+            DPR_CUDA_TRY(cudaGetLastError());
+            const bool hybrid = tp.rows < (int)a.grid[1];
+            set_last_path(DPR_OP_FORWARD, hybrid ? "tile2d_hybrid_radial_fixed" : (tp.exclusive ? "tile2d_radial_fixed" : "tile2d_split_radial_fixed"));
+            return DPR_OK;
+        }
+    }
     // Several slabs per pose: sort the points spatially once and let every slab CTA skip the 1024-point runs whose
     // bounding box cannot reach its rows (otherwise each of the S slabs would transform all P points).
     const float* pts = a.points;
@@ -587,7 +626,9 @@ template int forward_dispatch<double>(const ForwardArgs<double>&, const DeviceIn
 size_t forward_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t, int sizeof_T) {
     // point-weight statistics (256 B) + room for the spatially sorted copy of the points and their run boxes
     const SortPlan sp = make_sort_plan(n_in, P, sizeof_T, true, 256);
-    return sp.total + sizeof(float) * 2 * (size_t)n_in * (size_t)((P + 1023) / 1024) + 256;
+    const size_t morton = sp.total + sizeof(float) * 2 * (size_t)n_in * (size_t)((P + 1023) / 1024) + 256;
+    const size_t radial = make_radial_plan(P, 256).total + 256;
+    return morton > radial ? morton : radial;
 }
 
 }  // namespace dpr

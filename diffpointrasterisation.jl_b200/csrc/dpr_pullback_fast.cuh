@@ -118,9 +118,12 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
         valid[k] = p < P;
         const int pp = valid[k] ? p : 0;
         load_point(x[k], points, (int64_t)pp);
-        if (!valid[k]) {   // padding lanes: a far-away point has no in-bounds corner, so the loop needs no extra predicate
+        if (!valid[k]) {
+            // padding lanes sit on the origin (finite weights for every pose) and never load: all four corner
+            // predicates below include valid[k], so every contribution is an exact zero.  (A far-away point is NOT
+            // safe: a matrix row orthogonal to it - e.g. (1,-1,0)/sqrt(2) against (c,c,c) - projects it to the origin.)
 #pragma unroll
-            for (int j = 0; j < N_IN; ++j) x[k][j] = T(1e30);
+            for (int j = 0; j < N_IN; ++j) x[k][j] = T(0);
         }
         pw[k] = HAS_PW ? __ldg(point_weight + pp) : T(1);
 #pragma unroll
@@ -166,7 +169,7 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
             T dl[2];
             stencil2<T, N_IN>(x[k], R, neg_origin, scale, g, ix, iy, dl);
             // per-corner bounds rule (src/raster_pullback.jl:51) as four load predicates
-            const bool x_lo = (unsigned)ix < (unsigned)g[0], x_hi = (unsigned)(ix + 1) < (unsigned)g[0];
+            const bool x_lo = valid[k] && (unsigned)ix < (unsigned)g[0], x_hi = valid[k] && (unsigned)(ix + 1) < (unsigned)g[0];
             const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
             const int off = iy * g[0] + ix;          // 32-bit: the host guarantees g0*g1 < 2^30; OOB lanes never load
             T G00 = T(0), G10 = T(0), G01 = T(0), G11 = T(0);

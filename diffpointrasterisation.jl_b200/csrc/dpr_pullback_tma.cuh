@@ -97,16 +97,20 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
 
     // ===== consumer warps ======================================================================================
     float x[K][N_IN], pw[K], dpt[K][N_IN], dpw[K];
+    unsigned valid_mask = 0;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int p = (pc * K + k) * kTmaConsumers + (int)threadIdx.x;
         const bool valid = p < P;
+        valid_mask |= valid ? (1u << k) : 0u;
         const int pp = valid ? p : 0;
         load_point(x[k], points, (int64_t)pp);
         pw[k] = HAS_PW ? __ldg(point_weight + pp) : 1.f;
         if (!valid) {
+            // padding lanes sit on the origin and never load (corner predicates include the valid bit): exact zeros.
+            // A far-away point is not safe - a matrix row orthogonal to it projects it into the image.
 #pragma unroll
-            for (int j = 0; j < N_IN; ++j) x[k][j] = 1e30f;      // padding lanes: no in-bounds corner
+            for (int j = 0; j < N_IN; ++j) x[k][j] = 0.f;
         }
 #pragma unroll
         for (int j = 0; j < N_IN; ++j) dpt[k][j] = 0.f;
@@ -156,7 +160,8 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
                 int ix, iy;
                 float dl[2];
                 stencil2<float, N_IN>(x[k], R, neg_origin, scale, g, ix, iy, dl);
-                const bool x_lo = (unsigned)ix < (unsigned)g[0], x_hi = (unsigned)(ix + 1) < (unsigned)g[0];
+                const bool valid = (valid_mask >> k) & 1u;
+                const bool x_lo = valid && (unsigned)ix < (unsigned)g[0], x_hi = valid && (unsigned)(ix + 1) < (unsigned)g[0];
                 const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
                 const int off = iy * g[0] + ix;
                 float G00 = 0.f, G10 = 0.f, G01 = 0.f, G11 = 0.f;

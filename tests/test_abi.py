@@ -48,6 +48,11 @@ def test_fast_forward_kernel_has_no_packed_fma():
     for body in fast:
         assert "FFMA2" not in body
         assert "FMUL2" in body and "ATOMS.ADD" in body
+    radial = [c for c in chunks if "fwd_tile2d_radial_kernel" in c.split("\n", 1)[0]]
+    assert len(radial) == 4      # N_in in {2,3} x point weights
+    for body in radial:          # same rule; plus the streaming 16-byte point loads and the native integer atomics
+        assert "FFMA2" not in body
+        assert "FMUL2" in body and "ATOMS.ADD" in body and "LDG.E.NA.128" in body
     tma = [c for c in chunks if "pullback_tma2d_kernel" in c.split("\n", 1)[0]]
     assert len(tma) == 8
     for body in tma:   # TMA bulk copy + mbarrier pipeline really are in the SASS, and no packed FMA

@@ -139,6 +139,84 @@ def test_forward_slabs_with_chunk_culling(n_in):
     assert torch.equal(out, out2), "fixed-point accumulation is order independent: culling must not change a bit"
 
 
+@pytest.mark.parametrize("n_in", [2, 3])
+@pytest.mark.parametrize("weights", [True, False])
+@pytest.mark.parametrize("opts", [dict(), dict(point_split=1), dict(tile_smem_bytes=80 * 64 * 4, point_split=1), dict(point_split=3),
+                                  dict(point_split=2, tile_smem_bytes=84 * 64 * 4)])
+def test_forward_radial_path(n_in, weights, opts):
+    """Radius-sorted forward kernel (dpr_forward_radial.cuh): whole image on chip, hybrid band centred per pose, point
+    splits; poses whose matrix is NOT a rotation (scaled, sheared, zero), translations that push the cloud half out of
+    the image or out of the band, points far outside the cube, P not a multiple of the chunk length."""
+    grid = (64, 96)
+    P, B = 41003, 12
+    d = make_inputs(900 + n_in, n_in, 2, P, B, grid, np.float32, weights)
+    d["points"][:, :300] *= 5.0                       # far outside
+    d["points"][:, 300:310] = 0.0                     # radius exactly zero
+    d["rotation"][:, :, 1] *= 1.7                     # not orthonormal: the safe radius must use the row norms
+    d["rotation"][0, :, 2] += 0.5 * d["rotation"][1, :, 2]
+    d["rotation"][:, :, 3] = 0.0                      # every point lands on the projected origin
+    d["translation"][:, 4] = (0.9, -0.8)              # cloud mostly outside the image
+    d["translation"][:, 5] = (0.0, 0.55)              # cloud centred far from the middle rows (band follows it)
+    d["translation"][:, 6] = (0.0, -1.4)
+    out_ref, _ = _oracle_pair(d, grid, np.float32)
+    args = dev_args(d, np.float32)
+    with forced(forward_algo=2, point_sort=1, **opts):
+        out = dpr_b200.raster(grid, *args)
+        path = dpr_b200.last_path(0)
+        out2 = dpr_b200.raster(grid, *args)
+    assert "radial" in path, path
+    if "tile_smem_bytes" in opts:
+        assert "hybrid" in path, path
+    # pose 3 puts all 41003 points on one pixel: its cells wrap 32 bits, the CTA falls back to Float32 atomics, and
+    # 41003 sequential Float32 additions into one cell are only good to ~1e-3 (the reference's own Float32 path too)
+    keep = [b for b in range(B) if b != 3]
+    for b in range(B):     # every pose on its own: a broken pose must not hide behind the others
+        assert rel_l2(to_np(out)[:, :, b], out_ref[:, :, b]) <= (1e-5 if b != 3 else 2e-3), (path, b)
+    assert rel_l2(to_np(out)[:, :, keep], out_ref[:, :, keep]) <= 1e-5, path
+    if opts.get("point_split", 0) == 1 and "hybrid" not in path:
+        assert torch.equal(out[:, :, keep], out2[:, :, keep]), "integer accumulation must not depend on the order of the atomics"
+    with forced(forward_algo=2, point_sort=2, **opts):
+        old = dpr_b200.raster(grid, *args)
+        assert "radial" not in dpr_b200.last_path(0)
+    assert rel_l2(to_np(out)[:, :, keep], to_np(old)[:, :, keep]) <= 2e-6
+
+
+@pytest.mark.parametrize("case", ["wrap", "negative_out_weight", "negative_point_weight", "wide_dynamic_range", "zero_weight",
+                                  "tiny_weights", "huge_weights"])
+def test_forward_radial_fixed_point_fallbacks(case):
+    """The radial kernel's fixed-point mode (subnormal quantisation) on the inputs it must not mishandle."""
+    grid = (32, 32)
+    rng = np.random.default_rng(1)
+    P, B = 30000, 3
+    pts = np.asfortranarray((0.3 * rng.standard_normal((3, P))).astype(np.float32))
+    d = make_inputs(2, 3, 2, P, B, grid, np.float32)
+    ow, pw = d["out_weight"].copy(), None
+    if case == "wrap":
+        pts[:, :20000] = np.array([[0.013], [0.021], [0.0]], dtype=np.float32)   # 20000 points in one pixel
+    elif case == "negative_out_weight":
+        ow[1] = -ow[1]
+    elif case == "negative_point_weight":
+        pw = rng.standard_normal(P).astype(np.float32)
+    elif case == "wide_dynamic_range":
+        pw = np.exp(8 * rng.standard_normal(P)).astype(np.float32)
+    elif case == "zero_weight":
+        ow[0] = 0.0
+    elif case == "tiny_weights":
+        ow = (ow * 1e-10).astype(np.float32)
+        pw = (1e-12 * (0.5 + rng.random(P))).astype(np.float32)
+    elif case == "huge_weights":
+        ow = (ow * 1e12).astype(np.float32)
+        pw = (1e9 * (0.5 + rng.random(P))).astype(np.float32)
+    bg = None if case in ("tiny_weights", "huge_weights") else d["background"]     # a background would hide tiny splats
+    ref = oracle.raster(grid, pts, d["rotation"], d["translation"], bg, ow, pw, dtype=np.float32, f64_accumulate=True)
+    with forced(forward_algo=2, forward_accum=0, point_sort=1):
+        out = dpr_b200.raster(grid, *(to_dev(a) for a in (pts, d["rotation"], d["translation"], bg, ow, pw)))
+        assert "radial" in dpr_b200.last_path(0)
+    assert rel_l2(to_np(out), ref) <= 1e-5, case
+    big = np.abs(ref) > 1e-3 * np.abs(ref).max()
+    assert np.max(np.abs(to_np(out)[big] - ref[big]) / np.abs(ref[big])) < 2e-4, case
+
+
 @pytest.mark.parametrize("case", ["wrap", "negative_out_weight", "negative_point_weight", "wide_dynamic_range", "zero_weight"])
 def test_forward_fixed_point_fallbacks(case):
     """Inputs the fixed-point mode must not mishandle: a cell that wraps 32 bits (thousands of coincident points),
@@ -217,6 +295,37 @@ def test_pullback_paths_agree(dtype, n_in, weights):
                 assert dpr_b200.last_path(1).endswith("_sorted") == (sort == 1)
             for k in FIELDS:
                 assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (algo, sort, k)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_padding_lanes_never_contribute(dtype):
+    """P is not a multiple of any block size, and some pose matrices have a row orthogonal to (1,1,1) or are all zero:
+    a padding lane parked at a far-away point (c,c,c) would be projected INTO the image by such a row and pollute
+    d_rotation / d_translation / d_out_weight (found while writing the radial forward kernel)."""
+    grid = (32, 32)
+    n_in, P, B = 3, 1037, 20
+    d = make_inputs(4242, n_in, 2, P, B, grid, dtype, True)
+    s = 1 / np.sqrt(2)
+    d["rotation"][:, :, 0] = np.array([[s, -s, 0.0], [0.0, 0.0, 1.0]], dtype=dtype)
+    d["rotation"][:, :, 1] = np.array([[1.0, -1.0, 0.0], [0.5, 0.5, -1.0]], dtype=dtype)
+    d["rotation"][:, :, 2] = 0.0
+    out_ref, pb_ref = _oracle_pair(d, grid, dtype)
+    args = dev_args(d, dtype)
+    td = torch.float32 if dtype == np.float32 else torch.float64
+    ds = to_dev(d["ds_dout"], td)
+    algos = (0, 1, 2, 3, 4) if dtype == np.float32 else (0, 1, 2, 3)
+    for pa in algos:
+        with forced(pullback_algo=pa):
+            pb = dpr_b200.raster_pullback_(ds, *args)
+            path = dpr_b200.last_path(1)
+        for k in FIELDS:
+            assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (pa, path, k)
+    for fa, ps in ((0, 0), (1, 0), (2, 0), (2, 1), (2, 2)):
+        with forced(forward_algo=fa, point_sort=ps):
+            out = dpr_b200.raster(grid, *args)
+            path = dpr_b200.last_path(0)
+        for b in range(B):
+            assert rel_l2(to_np(out)[:, :, b], out_ref[:, :, b]) <= TOL[dtype], (fa, ps, path, b)
 
 
 def test_batched_equals_singles():
