@@ -531,7 +531,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     {
         const RadialPlan rp = make_radial_plan(a.P, 256);
         const int64_t ps = tuning().point_sort;
-        const bool want = ps == 1 || (ps == 0 && a.P >= 8192 && (double)a.P * (double)a.B >= 6.4e7);
+        const bool want = a.P >= 8192 && (ps == 1 || (ps == 0 && (double)a.P * (double)a.B >= 6.4e7));
         if (tp.slabs == 1 && want && a.workspace && a.workspace_bytes >= rp.total && a.P < (int64_t)0x3ffffc00) {
             int rc = radial_sort_points<N_IN>(a.points, a.point_weight, fp.pw_stats, a.P, a.workspace, rp, dev, a.stream);
             if (rc != DPR_OK) return rc;
@@ -627,7 +627,7 @@ size_t forward_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t
     // point-weight statistics (256 B) + room for the spatially sorted copy of the points and their run boxes
     const SortPlan sp = make_sort_plan(n_in, P, sizeof_T, true, 256);
     const size_t morton = sp.total + sizeof(float) * 2 * (size_t)n_in * (size_t)((P + 1023) / 1024) + 256;
-    const size_t radial = make_radial_plan(P, 256).total + 256;
+    const size_t radial = P >= 8192 ? make_radial_plan(P, 256).total + 256 : 0;   // radial kernel: large clouds only
     return morton > radial ? morton : radial;
 }
 
