@@ -303,7 +303,7 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     else:
         peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    fwd_names = [k for k in kernel_ms if k.startswith("fwd_splat")]
+    fwd_names = [k for k in kernel_ms if k.startswith("fwd_")]
     bwd_names = [k for k in kernel_ms if k.startswith("pullback_")]
     cand = {}
     if fwd_names:

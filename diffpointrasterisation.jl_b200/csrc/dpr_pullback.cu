@@ -11,6 +11,8 @@
 // splat); the per-pose point-sums are reduced with warp shuffles, combined per CTA in shared memory, and leave the
 // CTA as one REDG per (pose, value).  CTAs are ordered so that neighbours work on the same poses at the same time,
 // which keeps the ds_dout images they gather from resident in L1/L2.
+#include <cmath>
+
 #include "dpr_common.cuh"
 #include "dpr_internal.h"
 #include "dpr_sort.cuh"
@@ -290,6 +292,7 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 }  // namespace dpr
 #include "dpr_pullback_fast.cuh"
 #include "dpr_pullback_tma.cuh"
+#include "dpr_pullback_win.cuh"
 namespace dpr {
 
 // zero everything that is accumulated with REDG (the five fill! calls of ext/DiffPointRasterisationCUDAExt.jl:272-276)
@@ -456,6 +459,90 @@ static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, i
     return DPR_OK;
 }
 
+// Float32 images larger than shared memory: TMA-staged windows around the projected centroid of each CTA's points
+// (dpr_pullback_win.cuh).  Needs the spatially sorted copy of the points.
+constexpr int kWinK = 8;
+
+// rows per band for `stages` stages (0: the kernel does not apply)
+static int win_band_rows(const DeviceInfo& dev, int64_t g0, int64_t g1, int stages, int n_in) {
+    const int64_t fixed = (int64_t)win_pullback_smem(g0, 0, stages, n_in) + 1024;
+    int64_t rows = ((int64_t)dev.max_smem_optin - fixed) / stages / (g0 * 4);
+    if (rows > g1) rows = g1;
+    return rows >= 32 ? (int)rows : 0;
+}
+
+static size_t win_centroid_offset(int n_in, int64_t P, bool has_pw) {
+    return (make_sort_plan(n_in, P, 4, has_pw, 256).total + 255) / 256 * 256;
+}
+static size_t win_workspace_bytes(int n_in, int64_t P) {
+    const int64_t ppc = (int64_t)kTmaConsumers * kWinK;
+    return win_centroid_offset(n_in, P, true) + sizeof(float) * (size_t)n_in * (size_t)((P + ppc - 1) / ppc) + 256;
+}
+
+template <int N_IN>
+static int pullback_win2d(const PullbackArgs<float>& a, const DeviceInfo& dev) {
+    constexpr int K = kWinK;
+    Grid<float, 2> grid;
+    grid.cells = 1;
+    for (int k = 0; k < 2; ++k) {
+        grid.g[k] = (int)a.grid[k];
+        grid.scale[k] = float(a.grid[k]) / 2.f;
+        grid.cells *= a.grid[k];
+    }
+    int rc = zero_gradients(a);
+    if (rc != DPR_OK) return rc;
+    rc = launch_background_sum(a, grid.cells, dev);
+    if (rc != DPR_OK) return rc;
+    const bool has_pw = a.point_weight != nullptr;
+    const SortPlan sp = make_sort_plan(N_IN, a.P, 4, has_pw, 256);
+    rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+    if (rc != DPR_OK) return rc;
+    char* ws = static_cast<char*>(a.workspace);
+    const float* pts = reinterpret_cast<const float*>(ws + sp.off_points);
+    const float* pwt = has_pw ? reinterpret_cast<const float*>(ws + sp.off_pw) : nullptr;
+    const int32_t* perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
+    float* centroid = reinterpret_cast<float*>(ws + win_centroid_offset(N_IN, a.P, has_pw));
+    const int64_t ppc = (int64_t)kTmaConsumers * K;
+    const int64_t point_chunks = (a.P + ppc - 1) / ppc;
+    {
+        LaunchScope scope("chunk_centroid", a.stream);
+        chunk_centroid_kernel<N_IN><<<(unsigned)point_chunks, 256, 0, a.stream>>>(pts, a.P, (int)ppc, centroid);
+    }
+    // pose chunks: fill whole waves of one CTA per SM, keep chunks long enough to amortise the per-point REDGs
+    int64_t pose_chunks = 1;
+    if (tuning().pose_chunk > 0) {
+        pose_chunks = (a.B + tuning().pose_chunk - 1) / tuning().pose_chunk;
+    } else {
+        double best = 1e30;
+        for (int64_t m = 1; m <= 64 && m <= a.B; ++m) {
+            if (a.B / m < 32 && m > 1) break;
+            const int64_t n = point_chunks * m;
+            const int64_t waves = (n + dev.sm_count - 1) / dev.sm_count;
+            const double cost = (double)waves * dev.sm_count / (double)n + 0.01 * m;   // wave inefficiency + REDG overhead
+            if (cost < best) { best = cost; pose_chunks = m; }
+        }
+    }
+    const int64_t pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
+    pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
+    if (point_chunks * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
+    constexpr int stages = 2;   // measured on config 2: 2 stages x 108 rows 2.52 ms, 3 stages x 72 rows 3.38 ms
+    const int wy = win_band_rows(dev, a.grid[0], a.grid[1], stages, N_IN);
+    const size_t smem = win_pullback_smem(a.grid[0], wy, stages, N_IN);
+    auto launch = [&](auto kern) -> int {
+        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchScope scope("pullback_win2d", a.stream);
+        kern<<<(unsigned)(point_chunks * pose_chunks), kTmaConsumers + 32, smem, a.stream>>>(
+            a.ds_dout, pts, centroid, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
+            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk, wy);
+        return DPR_OK;
+    };
+    rc = has_pw ? launch(pullback_win2d_kernel<N_IN, K, true, 2>) : launch(pullback_win2d_kernel<N_IN, K, false, 2>);
+    if (rc != DPR_OK) return rc;
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_PULLBACK, "win2d_sorted");
+    return DPR_OK;
+}
+
 template <typename T>
 int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     if constexpr (sizeof(T) == 4) {
@@ -471,6 +558,24 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
             if (stages && worth) {
                 if (a.n_in == 2) return pullback_tma2d<2>(a, dev, stages);
                 if (a.n_in == 3) return pullback_tma2d<3>(a, dev, stages);
+            }
+        }
+        // windowed TMA kernel: larger images, rows a multiple of 16 bytes, the sorted copy of the points available
+        if (a.n_out == 2 && (algo == 0 || algo == 5) && (a.n_in == 2 || a.n_in == 3) && (a.grid[0] % 4) == 0 &&
+            a.grid[0] >= 8 && a.grid[1] >= 8 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 &&
+            a.P < (int64_t)0x3fffffff && a.B < (int64_t)0x7fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff &&
+            tuning().point_sort != 2 && a.workspace && a.workspace_bytes >= win_workspace_bytes(a.n_in, a.P) &&
+            win_band_rows(dev, a.grid[0], a.grid[1], 3, a.n_in) > 0) {
+            // Worth it when the band covers the projected blob of a CTA's point run: a run of ppc sorted points out of
+            // P spans about g1 * (ppc / P)^(1/n_in) rows.  Measured on B200: config 4 (1 M points, 2-d, 512^2: 32-row
+            // blobs, 54-row bands) 4.23 -> 3.58 ms; config 2 (100 k points, 3-d, 256^2: 86-row blobs, 108-row bands)
+            // 2.12 -> 2.57 ms, so sparse clouds stay on the L1-gather kernel.
+            const double blob_rows = (double)a.grid[1] * pow((double)kTmaConsumers * kWinK / (double)a.P, 1.0 / a.n_in);
+            const bool worth = algo == 5 || (a.P >= 4 * (int64_t)kTmaConsumers * kWinK && a.B >= 64 &&
+                                             a.grid[0] * a.grid[1] * 4 > (int64_t)96 * 1024 &&
+                                             (double)win_band_rows(dev, a.grid[0], a.grid[1], 2, a.n_in) >= 1.5 * blob_rows);
+            if (worth && a.P > 0 && a.B > 0) {
+                return a.n_in == 2 ? pullback_win2d<2>(a, dev) : pullback_win2d<3>(a, dev);
             }
         }
     }
@@ -491,7 +596,9 @@ template int pullback_dispatch<float>(const PullbackArgs<float>&, const DeviceIn
 template int pullback_dispatch<double>(const PullbackArgs<double>&, const DeviceInfo&);
 
 size_t pullback_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t, int sizeof_T) {
-    return make_sort_plan(n_in, P, sizeof_T, true, 256).total;
+    const size_t sorted = make_sort_plan(n_in, P, sizeof_T, true, 256).total;
+    const size_t win = sizeof_T == 4 ? win_workspace_bytes(n_in, P) : 0;
+    return sorted > win ? sorted : win;
 }
 
 }  // namespace dpr

@@ -277,6 +277,31 @@ def test_pullback_tma_staged_images(n_in, weights, B, pose_chunk):
             assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, (sort, k)
 
 
+@pytest.mark.parametrize("n_in", [2, 3])
+@pytest.mark.parametrize("weights", [True, False])
+@pytest.mark.parametrize("grid,B,pose_chunk", [((192, 160), 9, 0), ((192, 160), 150, 70), ((256, 400), 70, 0), ((64, 48), 20, 0)])
+def test_pullback_tma_staged_windows(n_in, weights, grid, B, pose_chunk):
+    """Float32 pose images larger than shared memory: per (CTA, pose) a band of full-width rows around the projected
+    centroid of the CTA's sorted points is staged by one TMA bulk copy; stencils outside the band (or touching the
+    left / right image border) take the global-load fallback through the same predicated generic loads.  Images taller
+    and shorter than the band, clouds pushed half out of the image, far-away points, matrices that are not rotations,
+    several rounds / pose chunks."""
+    P = 9001
+    d = make_inputs(4321 + B, n_in, 2, P, B, grid, np.float32, weights)
+    d["points"][:, :3] = np.array([[5.0, -7.0, 1e30], [0.99, -1.0, 1.0]] + ([[0.0, 0.0, 0.0]] if n_in == 3 else []), dtype=np.float32)
+    d["points"][:, 3:200] *= 2.5                      # a halo the window cannot cover: fallback loads
+    d["rotation"][:, :, 1] *= 1.6
+    d["rotation"][:, :, 2] = 0.0
+    d["translation"][:, 3] = (0.9, -0.8)
+    d["translation"][:, 4] = (-1.1, 0.2)
+    _, pb_ref = _oracle_pair(d, grid, np.float32)
+    with forced(pullback_algo=5, pose_chunk=pose_chunk):
+        pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], torch.float32), *dev_args(d, np.float32))
+        assert dpr_b200.last_path(1) == "win2d_sorted"
+    for k in FIELDS:
+        assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, k
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n_in", [2, 3])
 @pytest.mark.parametrize("weights", [True, False])
@@ -313,7 +338,7 @@ def test_padding_lanes_never_contribute(dtype):
     args = dev_args(d, dtype)
     td = torch.float32 if dtype == np.float32 else torch.float64
     ds = to_dev(d["ds_dout"], td)
-    algos = (0, 1, 2, 3, 4) if dtype == np.float32 else (0, 1, 2, 3)
+    algos = (0, 1, 2, 3, 4, 5) if dtype == np.float32 else (0, 1, 2, 3)
     for pa in algos:
         with forced(pullback_algo=pa):
             pb = dpr_b200.raster_pullback_(ds, *args)
@@ -407,7 +432,7 @@ def test_no_out_of_bounds_writes(dtype, n_in, n_out, grid):
         with forced(forward_algo=falgo):
             dpr_b200.raster_(out, *args)
         assert torch.all(buf[:pad] == sentinel) and torch.all(buf[-pad:] == sentinel), f"forward algo {falgo} wrote out of bounds"
-    palgos = (1, 2, 3, 4) if (n_out == 2 and dtype == np.float32) else ((1, 2) if n_out == 2 else (1,))
+    palgos = (1, 2, 3, 4, 5) if (n_out == 2 and dtype == np.float32) else ((1, 2) if n_out == 2 else (1,))
     for palgo in palgos:
         shapes = dict(points_out=(n_in, P), rotation_out=(n_out, n_in, B), translation_out=(n_out, B),
                       background_out=(B,), out_weight_out=(B,), point_weight_out=(P,))
@@ -555,7 +580,7 @@ def test_randomised_shapes_and_misaligned_buffers():
             assert rel_l2(to_np(out), out_ref) <= TOL[dtype], (trial, "fwd", fa, grid, P, B)
         palgos = (0, 1, 2, 3) if n_out == 2 else (0, 1)
         if n_out == 2 and dtype == np.float32 and (grid[0] * grid[1]) % 4 == 0:
-            palgos += (4,)
+            palgos += (4, 5)       # 5 (windowed TMA) needs 16-byte rows and aligned images, else the library falls through
         for pa in palgos:
             with forced(pullback_algo=pa):
                 pb = dpr_b200.raster_pullback_(ds, *args)
