@@ -281,6 +281,7 @@ def main():
     total_ms = ev[0].elapsed_time(ev[1])
     records = _lib.profile_records()
     _lib.profile_enable(False)
+    paths = (dpr_b200.last_path(0), dpr_b200.last_path(1))      # of the timed steps (the e2e leg below runs pose chunks)
     launches = dpr_b200.kernel_launch_count() - launches0
     sampler.join(timeout=1.0)
     if world > 1:
@@ -397,7 +398,7 @@ def main():
                                 parallelism=f"pose-sharded x{world}, points replicated, 1 all-reduce of d_points+d_point_weight",
                                 collective=comm_kind,
                                 l2="inputs larger than L2 (out and ds_dout are 1.07 GB each per step; no flush needed)",
-                                forward_path=dpr_b200.last_path(0), pullback_path=dpr_b200.last_path(1)),
+                                forward_path=paths[0], pullback_path=paths[1]),
                     kernels_ms=kernel_ms, fwd_splats_per_s=(P * B * world / (sum(kernel_ms[k] for k in kernel_ms if k.startswith("fwd_") or k == "fill_background") * 1e-3)) if do_fwd else None,
                     roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=launches, clocks=sampler.result())
         print(json.dumps(line), flush=True)
