@@ -181,6 +181,43 @@ def test_forward_radial_path(n_in, weights, opts):
     assert rel_l2(to_np(out)[:, :, keep], to_np(old)[:, :, keep]) <= 2e-6
 
 
+def test_forward_radial_randomised_and_non_finite_poses():
+    """Random shapes through the radius-sorted kernel (odd grid extents, P just above its threshold and not a multiple
+    of the chunk length, few and many poses, sliced buffers), plus poses with NaN / Inf entries: those may produce
+    anything for themselves but must not disturb their neighbours or crash the launch."""
+    rng = np.random.default_rng(77)
+    for trial in range(10):
+        n_in = 2 + trial % 2
+        grid = (int(rng.integers(9, 150)), int(rng.integers(9, 200)))
+        P, B = int(rng.integers(8192, 26000)), int(rng.integers(1, 48))
+        weights = bool(trial % 3)
+        d = make_inputs(5000 + trial, n_in, 2, P, B, grid, np.float32, weights)
+        d["translation"] *= 3.0                                  # many clouds partly or wholly outside
+        d["rotation"] *= rng.uniform(0.2, 2.5, size=(1, 1, B)).astype(np.float32)
+        out_ref, _ = _oracle_pair(d, grid, np.float32)
+        args = dev_args(d, np.float32)
+        with forced(forward_algo=2, point_sort=1):
+            out = dpr_b200.raster(grid, *args)
+            path = dpr_b200.last_path(0)
+        assert "radial" in path or "slabs" in path or path.startswith("global"), path
+        for b in range(B):
+            assert rel_l2(to_np(out)[:, :, b], out_ref[:, :, b]) <= 1e-5, (trial, path, grid, P, B, b)
+    # non-finite poses
+    grid = (64, 64)
+    d = make_inputs(31337, 3, 2, 12000, 6, grid, np.float32, True)
+    d["rotation"][0, 1, 1] = np.nan
+    d["translation"][1, 3] = np.inf
+    d["rotation"][:, :, 4] = 1e30
+    good = [0, 2, 5]
+    ref = oracle.raster(grid, d["points"], d["rotation"][:, :, good], d["translation"][:, good], d["background"][good],
+                        d["out_weight"][good], d["point_weight"], dtype=np.float32, f64_accumulate=True)
+    with forced(forward_algo=2, point_sort=1):
+        out = dpr_b200.raster(grid, *dev_args(d, np.float32))
+        assert "radial" in dpr_b200.last_path(0)
+    torch.cuda.synchronize()
+    assert rel_l2(to_np(out)[:, :, good], ref) <= 1e-5      # the bad poses' own images are unspecified
+
+
 @pytest.mark.parametrize("case", ["wrap", "negative_out_weight", "negative_point_weight", "wide_dynamic_range", "zero_weight",
                                   "tiny_weights", "huge_weights"])
 def test_forward_radial_fixed_point_fallbacks(case):
