@@ -145,8 +145,10 @@ constexpr int kMagicBits = 0x4B400000;
 template <typename T, int N_IN, typename Loader>
 __device__ __forceinline__ void tile_accumulate_with(T* __restrict__ tile, T* __restrict__ img, Loader load,
                                                      const Pose<T, N_IN, 2>& pose, const Grid<T, 2>& grid, int p_begin,
-                                                     int p_end, int ys, int ye, int band_lo, int band_hi, bool do_border) {
+                                                     int p_end, int ys, int ye, int band_lo, int band_hi, bool do_border,
+                                                     int pitch = 0) {
     const int g0 = grid.g[0], g1 = grid.g[1];
+    if (pitch == 0) pitch = g0;                  // words per tile row (a skewed pitch spreads compact blobs over banks)
     const int nrows = ye - ys;
     int p = p_begin + threadIdx.x;
     T xn[N_IN], pwn = T(1);
@@ -172,11 +174,11 @@ __device__ __forceinline__ void tile_accumulate_with(T* __restrict__ tile, T* __
         auto tile_add = [&](int off, T v) { atomicAdd(tile + off, v); };
         if ((unsigned)i0[0] < (unsigned)(g0 - 1) && (unsigned)ry < (unsigned)(nrows - 1)) {
             // interior of the slab: all four corners are in bounds and on chip
-            const int off = ry * g0 + i0[0];
+            const int off = ry * pitch + i0[0];
             tile_add(off, v00);
             tile_add(off + 1, v10);
-            tile_add(off + g0, v01);
-            tile_add(off + g0 + 1, v11);
+            tile_add(off + pitch, v01);
+            tile_add(off + pitch + 1, v11);
         } else {
             const bool x_lo = i0[0] >= 0, x_hi = i0[0] + 1 < g0;
 #pragma unroll
@@ -185,7 +187,7 @@ __device__ __forceinline__ void tile_accumulate_with(T* __restrict__ tile, T* __
                 if (iy < 0 || iy >= g1) continue;                       // per-corner bounds rule, src/raster.jl:62
                 const T va = cy ? v01 : v00, vb = cy ? v11 : v10;
                 if (iy >= ys && iy < ye) {
-                    const int off = (iy - ys) * g0 + i0[0];
+                    const int off = (iy - ys) * pitch + i0[0];
                     if (x_lo) tile_add(off, va);
                     if (x_hi) tile_add(off + 1, vb);
                 } else if (do_border && (iy < band_lo || iy >= band_hi)) {
@@ -203,12 +205,12 @@ template <typename T, int N_IN>
 __device__ __forceinline__ void tile_accumulate(T* __restrict__ tile, T* __restrict__ img, const T* __restrict__ points,
                                                 const T* __restrict__ point_weight, const Pose<T, N_IN, 2>& pose,
                                                 const Grid<T, 2>& grid, int p_begin, int p_end, int ys, int ye,
-                                                int band_lo, int band_hi, bool do_border) {
+                                                int band_lo, int band_hi, bool do_border, int pitch = 0) {
     auto load = [&](int p, T (&x)[N_IN], T& pw) {
         load_point(x, points, (int64_t)p);
         if (point_weight) pw = __ldg(point_weight + p);
     };
-    tile_accumulate_with<T, N_IN>(tile, img, load, pose, grid, p_begin, p_end, ys, ye, band_lo, band_hi, do_border);
+    tile_accumulate_with<T, N_IN>(tile, img, load, pose, grid, p_begin, p_end, ys, ye, band_lo, band_hi, do_border, pitch);
 }
 
 __device__ __forceinline__ long long block_sum_ll(long long v, long long* scratch) {
@@ -507,6 +509,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     FastTileParams fp;
     fp.slabs = tp.slabs; fp.splits = tp.splits; fp.rows = tp.rows; fp.band_lo = tp.band_lo; fp.band_hi = tp.band_hi;
     fp.exclusive = tp.exclusive; fp.fixed_bits = tp.fixed_bits; fp.pw_stats = nullptr; fp.aabb = nullptr;
+    fp.pitch = (int)a.grid[0];
     const int64_t per_split = ((a.P + tp.splits - 1) / tp.splits + kChunk - 1) / kChunk * kChunk;
     fp.per_split = (int)per_split;
     const bool has_pw = a.point_weight != nullptr;
@@ -575,6 +578,17 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
             chunk_aabb_kernel<float, N_IN><<<(unsigned)n_runs, 256, 0, a.stream>>>(pts, a.P, kChunk, aabb);
         }
         fp.aabb = aabb;
+        // Sorted points put the 32 lanes of a warp into a blob a few pixels wide; with a row pitch that is a multiple of
+        // the 32 banks the bank depends on the column only and such a blob serialises 4-8 ways (profiles/
+        // probe_atomics_r01.json: coherent lanes 1.3 T/s at pitch 128 against 2.2 T/s at pitch 220).  Four padding words
+        // per row make the bank (x + 4 y) mod 32.
+        if ((a.grid[0] % 32) == 0) {
+            const size_t padded = ((size_t)tp.rows * (size_t)(a.grid[0] + 4) * 4 + 127) / 128 * 128 + fast_extra_smem(true) + 128;
+            if (padded <= (size_t)dev.max_smem_optin) {
+                fp.pitch = (int)a.grid[0] + 4;
+                smem_bytes = padded;
+            }
+        }
     }
     const int64_t ctas = a.B * tp.slabs * tp.splits;
     auto launch = [&](auto kern) -> int {

@@ -28,6 +28,7 @@ struct FastTileParams {
     int per_split;             // points per split, a multiple of kChunk
     const float* pw_stats;     // {max, min, mean} of point_weight or NULL
     const float* aabb;         // per-kChunk bounding boxes of the (spatially sorted) points, or NULL: no culling
+    int pitch;                 // words per tile row: g0, or g0 + 4 (bank skew for spatially sorted points)
 };
 
 // shared-memory carve-up (bytes) after the tile
@@ -55,8 +56,9 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
     const int ys = tp.band_lo + s * tp.rows;
     const int ye = (ys + tp.rows < tp.band_hi) ? ys + tp.rows : tp.band_hi;
     const int nrows = ye - ys;
-    const int n_tile = nrows * g0;
-    const int tile_cap = tp.rows * g0;                       // carve-up is the same for every CTA of the launch
+    const int pitch = tp.pitch;
+    const int n_tile = nrows * pitch;                        // incl. the padding words of every row (they stay zero)
+    const int tile_cap = tp.rows * pitch;                    // carve-up is the same for every CTA of the launch
     unsigned* tile_u = reinterpret_cast<unsigned*>(smem_raw);
     float* tile_f = reinterpret_cast<float*>(smem_raw);
     unsigned char* after = smem_raw + (((size_t)tile_cap * 4 + 127) / 128) * 128;
@@ -141,7 +143,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                 const int iy = i0[1] + cy;
                 if (iy < 0 || iy >= g1) continue;
                 if (iy >= ys && iy < ye) {
-                    const int off = (iy - ys) * g0 + i0[0];
+                    const int off = (iy - ys) * pitch + i0[0];
                     if (x_lo) tile_add(off, (w[2 * cy] * weight) * qscale);
                     if (x_hi) tile_add(off + 1, (w[2 * cy + 1] * weight) * qscale);
                 } else if (do_border && (iy < tp.band_lo || iy >= tp.band_hi)) {
@@ -235,11 +237,11 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
             if (interior) {
                 const float wq = HAS_PW ? wq_pose * pw : wq_pose;
                 const float a = du.y * wq, bq = dl.y * wq;
-                const int off = ry * g0 + ix;
+                const int off = ry * pitch + ix;
                 tile_add(off, du.x * a);
                 tile_add(off + 1, dl.x * a);
-                tile_add(off + g0, du.x * bq);
-                tile_add(off + g0 + 1, dl.x * bq);
+                tile_add(off + pitch, du.x * bq);
+                tile_add(off + pitch + 1, dl.x * bq);
             }
             // ---- defer the lanes that are not interior but touch this CTA's cells (warp-level compaction) ------
             bool slow = active && !interior;
@@ -279,34 +281,44 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
             for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile_f[i] = 0.f;
             __syncthreads();
             tile_accumulate<float, N_IN>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
-                                         tp.band_hi, false);
+                                         tp.band_hi, false, pitch);
             __syncthreads();
         }
     } else {
         tile_accumulate<float, N_IN>(tile_f, img, points, point_weight, pose, grid, p_begin, p_end, ys, ye, tp.band_lo,
-                                     tp.band_hi, do_border);
+                                     tp.band_hi, do_border, pitch);
         __syncthreads();
     }
 
+    // flush row by row (the tile pitch may differ from the image's): a warp per row, 16-byte accesses where aligned
     auto cell_value = [&](int i) -> float { return fixed ? (float)tile_u[i] * inv_qscale : tile_f[i]; };
     float* __restrict__ dst = img + (int64_t)ys * g0;
-    if (tp.exclusive) {
-        if ((n_tile & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
-            for (int i = threadIdx.x; i < n_tile / 4; i += blockDim.x) {
-                float4 v;
-                v.x = cell_value(4 * i) + bg;
-                v.y = cell_value(4 * i + 1) + bg;
-                v.z = cell_value(4 * i + 2) + bg;
-                v.w = cell_value(4 * i + 3) + bg;
-                reinterpret_cast<float4*>(dst)[i] = v;
+    const bool vec = (g0 & 3) == 0 && (pitch & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0;
+    for (int r = warp; r < nrows; r += 32) {
+        float* __restrict__ drow = dst + (int64_t)r * g0;
+        const int t0 = r * pitch;
+        if (tp.exclusive) {
+            if (vec) {
+                for (int c = lane; c < g0 / 4; c += 32) {
+                    float4 v;
+                    if (fixed) {
+                        const uint4 q4 = reinterpret_cast<const uint4*>(tile_u + t0)[c];
+                        v = make_float4(fmaf((float)q4.x, inv_qscale, bg), fmaf((float)q4.y, inv_qscale, bg),
+                                        fmaf((float)q4.z, inv_qscale, bg), fmaf((float)q4.w, inv_qscale, bg));
+                    } else {
+                        const float4 f4 = reinterpret_cast<const float4*>(tile_f + t0)[c];
+                        v = make_float4(f4.x + bg, f4.y + bg, f4.z + bg, f4.w + bg);
+                    }
+                    reinterpret_cast<float4*>(drow)[c] = v;
+                }
+            } else {
+                for (int c = lane; c < g0; c += 32) drow[c] = cell_value(t0 + c) + bg;
             }
         } else {
-            for (int i = threadIdx.x; i < n_tile; i += blockDim.x) dst[i] = cell_value(i) + bg;
-        }
-    } else {
-        for (int i = threadIdx.x; i < n_tile; i += blockDim.x) {
-            const float v = cell_value(i);
-            if (v != 0.f) red_add(dst + i, v);
+            for (int c = lane; c < g0; c += 32) {
+                const float v = cell_value(t0 + c);
+                if (v != 0.f) red_add(drow + c, v);
+            }
         }
     }
 }
