@@ -48,6 +48,29 @@ CONFIGS = {
     "readme5": dict(n_in=3, n_out=3, P=100_000, B=1, grid=(1024, 1024, 1024), dtype="f64", weights=False, ops="fwd+bwd",
                     label="README.md:193: 3d->3d, 100k points x 1 image, 1024^3, Float64"),
 }
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner to stdout when
+    NCCL_DEBUG is set on the box), so fd 1 is pointed at stderr for the whole run and the result line goes to the saved
+    descriptor."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 METRIC = "splats/sec (points x poses), forward + pullback"
 UNIT = "splats/s"
 
@@ -188,7 +211,7 @@ def run_reference(args, cfg):
                                   bwd_splats_per_s=cfg["P"] * n_poses / tb,
                                   note="Julia absent: C/OpenMP restatement of the reference's CPU algorithm (oracle/)"),
                 e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -205,6 +228,7 @@ def main():
     ap.add_argument("--ref-poses", type=int, default=512, help="poses per step of the --impl reference arm")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
+    claim_stdout()
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":
@@ -401,7 +425,7 @@ def main():
                                 forward_path=paths[0], pullback_path=paths[1]),
                     kernels_ms=kernel_ms, fwd_splats_per_s=(P * B * world / (sum(kernel_ms[k] for k in kernel_ms if k.startswith("fwd_") or k == "fill_background") * 1e-3)) if do_fwd else None,
                     roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=launches, clocks=sampler.result())
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
