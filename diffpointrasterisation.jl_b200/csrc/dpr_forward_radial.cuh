@@ -19,8 +19,11 @@
 //   * Hybrid mode (image a little larger than shared memory): the band of rows kept on chip is centred on the
 //     projected origin of EACH pose instead of the image centre, which is where the cloud is.
 //
-// Accumulation, wrap detection and flush are those of dpr_forward_fast.cuh (fixed point on the native ATOMS.ADD,
-// 64-bit mass checksum, float CAS fallback).
+// Accumulation is fixed point on the native ATOMS.ADD with the 64-bit mass checksum and the float CAS fallback of
+// dpr_forward_fast.cuh, but the integers are produced by a subnormal product instead of a conversion (see the kernel)
+// and the tile is flushed in one pass (checksum + conversion + store from one conflict-free 16-byte read).
+// Measured on config 2 (B200): 114 -> 69 instructions per warp-splat, 1.73 -> 1.57 ms; the kernel is then bound by the
+// shared-memory data pipe (3.95 wavefronts per ATOMS.ADD from random bank conflicts), see DESIGN.md 4.1b.
 #pragma once
 #include "dpr_common.cuh"
 #include "dpr_sort.cuh"
