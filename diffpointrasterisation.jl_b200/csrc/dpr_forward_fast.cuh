@@ -64,7 +64,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
     unsigned char* after = smem_raw + (((size_t)tile_cap * 4 + 127) / 128) * 128;
     int* queue = reinterpret_cast<int*>(after);
     int* clist = queue + 32 * kQueueCap;             // chunks of the current round that can touch this slab
-    __shared__ int s_count;
+    __shared__ int s_count, s_count_inner;
     float* __restrict__ img = out + b * grid.cells;
     const float bg = background ? __ldg(background + b) : 0.f;
     const bool border = (tp.band_lo > 0 || tp.band_hi < g1);
@@ -160,33 +160,95 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         for (int round = 0; round < n_chunks; round += (CULL ? kChunk : n_chunks)) {
         // ---- which chunks of this round can touch the slab?  (spatially sorted points + per-chunk boxes) ----------
         int n_iter = CULL ? ((n_chunks - round < kChunk) ? n_chunks - round : kChunk) : n_chunks;
+        int n_inner = 0;          // CULL: runs whose points are ALL interior to this slab (list grows from the front)
         if constexpr (CULL) {
-            if (threadIdx.x == 0) s_count = 0;
+            if (threadIdx.x == 0) { s_count = 0; s_count_inner = 0; }
             __syncthreads();
             const int c = round + (int)threadIdx.x;
-            bool keep = false;
+            bool keep = false, inner = false;
             if (c < n_chunks) {
                 const float* bx = tp.aabb + ((int64_t)(p_begin / kChunk) + c) * 2 * N_IN;
-                float cy = -pose.origin[1], hy = 0.f;
+                float cx = -pose.origin[0], hx = 0.f, cy = -pose.origin[1], hy = 0.f;
 #pragma unroll
                 for (int j = 0; j < N_IN; ++j) {
-                    cy = fmaf(pose.R[1][j], __ldg(bx + j), cy);
-                    hy = fmaf(fabsf(pose.R[1][j]), __ldg(bx + N_IN + j), hy);
+                    const float bc = __ldg(bx + j), bh = __ldg(bx + N_IN + j);
+                    cx = fmaf(pose.R[0][j], bc, cx);
+                    hx = fmaf(fabsf(pose.R[0][j]), bh, hx);
+                    cy = fmaf(pose.R[1][j], bc, cy);
+                    hy = fmaf(fabsf(pose.R[1][j]), bh, hy);
                 }
+                cx *= grid.scale[0];
                 cy *= grid.scale[1];
-                hy = hy * grid.scale[1] + 1.0f + 1e-3f * fabsf(cy);      // conservative: one row + rounding slack
-                // a point at row coordinate y touches rows [y - 1.5, y + 0.5]
-                keep = !(cy + hy + 0.5f < (float)ys) && !(cy - hy - 1.5f > (float)(ye - 1));
+                hx = hx * grid.scale[0] + 0.05f + 1e-3f * fabsf(cx);     // extent of the projected box + rounding slack
+                hy = hy * grid.scale[1] + 0.05f + 1e-3f * fabsf(cy);
+                // a point at row coordinate y touches rows [y - 1.5, y + 0.5]; one more row of slack for the culling
+                keep = !(cy + hy + 1.5f < (float)ys) && !(cy - hy - 2.5f > (float)(ye - 1));
+                // every point of a full run has all four corners on chip iff the projected box satisfies
+                // 0.5 < x <= g0 - 0.5 and ys + 0.5 < y <= ye - 0.5
+                inner = keep && p_begin + (c + 1) * kChunk <= p_end && cx - hx > 0.5f && cx + hx < (float)g0 - 0.5f &&
+                        cy - hy > (float)ys + 0.5f && cy + hy < (float)ye - 0.5f;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, keep);
-            int base = 0;
-            if (lane == 0 && m) base = atomicAdd(&s_count, __popc(m));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (keep) clist[base + __popc(m & ((1u << lane) - 1u))] = c;
+            // two lists in the same array: inner runs from the front, the others from the back
+            const bool mixed = keep && !inner;
+            const unsigned mi = __ballot_sync(0xffffffffu, inner), mm = __ballot_sync(0xffffffffu, mixed);
+            int bi = 0, bm = 0;
+            if (lane == 0 && mi) bi = atomicAdd(&s_count_inner, __popc(mi));
+            if (lane == 0 && mm) bm = atomicAdd(&s_count, __popc(mm));
+            bi = __shfl_sync(0xffffffffu, bi, 0);
+            bm = __shfl_sync(0xffffffffu, bm, 0);
+            if (inner) clist[bi + __popc(mi & ((1u << lane) - 1u))] = c;
+            if (mixed) clist[kChunk - 1 - (bm + __popc(mm & ((1u << lane) - 1u)))] = c;
             __syncthreads();
             n_iter = s_count;
+            n_inner = s_count_inner;
         }
-        auto chunk_of = [&](int i) -> int { if constexpr (CULL) return clist[i]; else return round + i; };
+        if constexpr (CULL) {
+            // ---- runs that are interior as a whole: no activity / bounds / slab test, no ballot, no queue ---------
+            float xi[N_IN], pwi = 1.f;
+            if (n_inner > 0) {
+                const int p0 = p_begin + clist[0] * kChunk + (int)threadIdx.x;
+                load_point(xi, points, (int64_t)p0);
+                if (HAS_PW) pwi = __ldg(point_weight + p0);
+            }
+            for (int it0 = 0; it0 < n_inner; it0 += 64) {
+                const int it1 = (it0 + 64 < n_inner) ? it0 + 64 : n_inner;
+#pragma unroll 2
+                for (int it = it0; it < it1; ++it) {
+                    float x[N_IN];
+#pragma unroll
+                    for (int j = 0; j < N_IN; ++j) x[j] = xi[j];
+                    const float pw = pwi;
+                    if (it + 1 < n_inner) {
+                        const int pn = p_begin + clist[it + 1] * kChunk + (int)threadIdx.x;
+                        load_point(xi, points, (int64_t)pn);
+                        if (HAS_PW) pwi = __ldg(point_weight + pn);
+                    }
+                    float2 prod[N_IN];
+#pragma unroll
+                    for (int j = 0; j < N_IN; ++j) prod[j] = __fmul2_rn(Rj[j], make_float2(x[j], x[j]));
+                    float s0 = prod[0].x, s1 = prod[0].y;
+#pragma unroll
+                    for (int j = 1; j < N_IN; ++j) { s0 = __fadd_rn(s0, prod[j].x); s1 = __fadd_rn(s1, prod[j].y); }
+                    const float2 coord = __fmul2_rn(__fadd2_rn(make_float2(s0, s1), neg_origin), scale2);
+                    const float2 r = make_float2(ceilf(__fadd_rn(coord.x, -0.5f)), ceilf(__fadd_rn(coord.y, -0.5f)));
+                    const float2 t = __fadd2_rn(r, make_float2(-0.5f, -0.5f));
+                    const float2 dl = make_float2(__fsub_rn(coord.x, t.x), __fsub_rn(coord.y, t.y));
+                    const float2 du = __fadd2_rn(make_float2(1.f, 1.f), make_float2(-dl.x, -dl.y));
+                    const int ix = __float2int_rn(r.x) - 1, iy = __float2int_rn(r.y) - 1;
+                    const float wq = HAS_PW ? wq_pose * pw : wq_pose;
+                    const float a = du.y * wq, bq = dl.y * wq;
+                    const int off = (iy - ys) * pitch + ix;
+                    tile_add(off, du.x * a);
+                    tile_add(off + 1, dl.x * a);
+                    tile_add(off + pitch, du.x * bq);
+                    tile_add(off + pitch + 1, dl.x * bq);
+                }
+                mass += mass32;
+                mass32 = 0;
+            }
+        }
+        // chunk of iteration i of the checked loop (with culling: the list that grows from the back)
+        auto chunk_of = [&](int i) -> int { if constexpr (CULL) return clist[kChunk - 1 - i]; else return round + i; };
         // software pipeline: the point of the next chunk is loaded while the current one is processed
         float xn[N_IN], pwn = 1.f;
         if (n_iter > 0) {
