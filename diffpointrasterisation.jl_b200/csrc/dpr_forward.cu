@@ -117,13 +117,14 @@ fwd_splat_global_kernel(const T* __restrict__ points, const T* __restrict__ rota
 //
 // Two accumulation modes for the shared-memory tile:
 //   float CAS    atomicAdd(float*) on shared memory = LDS + ATOMS.CAST.SPIN loop on sm_100a (no native f32 smem add)
-//   fixed point  (Float32, non-negative weights) contributions are quantised to q = rint(v * 2^F / cmax2) with
-//                cmax2 = the power of two >= out_weight * max(point_weight) and added with the NATIVE 32-bit
-//                ATOMS.ADD (3.4x the CAS rate, profiles/probe_atomics_r01.json).  Integer addition is exact, so the
-//                only error is the quantisation (<= 2^-(F+1) of the largest contribution per splat, F >= 18), and the
-//                result is independent of the order of the atomics.  Wrap-around of a 32-bit cell is detected exactly
-//                by a mass checksum (sum of all quantised contributions == sum of all cells); the CTA then redoes
-//                its slab with the float CAS mode.
+//   fixed point  (Float32, non-negative weights) a contribution w * out_weight * point_weight is accumulated as the
+//                integer rint(w * pw' * Q) (pw' = point weight scaled into [0, 1], 2^(F-1) <= Q <= 2^F, F <= 22) with the
+//                NATIVE 32-bit ATOMS.ADD (3.4x the CAS rate, profiles/probe_atomics_r01.json).  The integer is the bit
+//                pattern of a subnormal product - no conversion instruction (dpr_forward_fast.cuh).  Integer addition
+//                is exact, so the only error is the quantisation (about 2^-F of the largest contribution per splat)
+//                and the result is independent of the order of the atomics.  Wrap-around of a 32-bit cell is detected
+//                exactly by a mass checksum (sum of all quantised contributions == sum of all cells); the CTA then
+//                redoes its slab with the float CAS mode.
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct TileParams {
@@ -136,8 +137,6 @@ struct TileParams {
     int fixed_bits;   // planning only: fractional bits F for the Float32 fixed-point kernel (dpr_forward_fast.cuh)
 };
 
-constexpr float kMagic = 12582912.0f;      // 1.5 * 2^23: adding it leaves rint(x) in the low mantissa bits
-constexpr int kMagicBits = 0x4B400000;
 
 // Generic slab accumulation with shared-memory atomicAdd in the element type (CAS loop on sm_100a): used for Float64
 // and as the fallback of the Float32 fixed-point kernel.

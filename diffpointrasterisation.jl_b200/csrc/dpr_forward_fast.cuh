@@ -22,6 +22,26 @@ namespace dpr {
 constexpr int kChunk = 1024;          // points per chunk = threads per CTA = length of a culling run
 constexpr int kQueueCap = 64;         // per-warp deferred-point queue (ints)
 
+// Fixed-point scale.  A contribution v = w * out_weight * point_weight = w * pw' * A with pw' = point_weight * 2^-em in
+// [0, 1] (2^em >= max(point_weight); power-of-two scaling is exact) and A = out_weight * 2^em is accumulated as the integer
+// rint(w * pw' * Q), Q = rint(A * 2^(F - e)), 2^e >= A, so 2^(F-1) <= Q <= 2^F.  The integer is produced WITHOUT a
+// conversion: multiplying by Q * 2^-149 (the subnormal whose bit pattern is the integer Q) lands the product in the
+// subnormal range, where round-to-nearest leaves exactly rint(.) in the mantissa bits - __float_as_int of the product
+// IS the fixed-point value.  The rounding of Q is undone exactly at the flush (inv_q = A / Q).
+__device__ __forceinline__ int point_weight_exponent(const float* __restrict__ pw_stats) {
+    if (!pw_stats) return 0;
+    const float wmax = __ldg(pw_stats);
+    int em = 0;
+    if (wmax > 0.f && wmax < 3e38f) frexpf(wmax, &em);
+    return em;
+}
+// shared-memory reduction without return value on a 32-bit shared address (ATOMS.ADD RZ): keeps the address
+// arithmetic in 32 bits and out of the generic-pointer conversion the compiler otherwise repeats per iteration
+__device__ __forceinline__ void red_shared_u32(uint32_t addr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+
+
 struct FastTileParams {
     int slabs, splits, rows, band_lo, band_hi, exclusive;
     int fixed_bits;
@@ -77,23 +97,25 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
     const int p_begin = q * tp.per_split;
     const int p_end = (p_begin + tp.per_split < P) ? p_begin + tp.per_split : P;
 
-    // fixed-point scale (uniform across the CTA); not eligible -> float CAS accumulation through the generic code
+    // fixed-point scale (uniform across the CTA, see point_weight_exponent above); not eligible -> float CAS accumulation
     bool fixed = false;
-    float qscale = 0.f, inv_qscale = 0.f;
+    float wq_den = 0.f, inv_qscale = 0.f;
+    const int em = point_weight_exponent(HAS_PW ? tp.pw_stats : nullptr);
+    const float pw_scale = ldexpf(1.0f, -em);
     {
-        float cmax = pose.ow;
-        bool ok = cmax > 0.f;
+        bool ok = pose.ow > 0.f;
         if (HAS_PW) {
             const float wmax = __ldg(tp.pw_stats), wmin = __ldg(tp.pw_stats + 1), wmean = __ldg(tp.pw_stats + 2);
-            ok = ok && wmin >= 0.f && wmax > 0.f && wmax <= 64.f * wmean;
-            cmax *= wmax;
+            ok = ok && wmin >= 0.f && wmax > 0.f && wmax < 3e38f && wmax <= 64.f * wmean;
         }
-        ok = ok && cmax > 1e-30f && cmax < 1e30f;
+        const float A = ldexpf(pose.ow, em);
+        ok = ok && A > 1e-30f && A < 1e30f;
         if (ok) {
             int e;
-            frexpf(cmax, &e);                                  // cmax <= 2^e
-            qscale = ldexpf(1.0f, tp.fixed_bits - e);
-            inv_qscale = ldexpf(1.0f, e - tp.fixed_bits);
+            frexpf(A, &e);                                     // A <= 2^e
+            const float Q = rintf(ldexpf(A, tp.fixed_bits - e));   // 2^(F-1) <= Q <= 2^F <= 2^22
+            wq_den = __int_as_float((int)Q);
+            inv_qscale = A / Q;
             fixed = true;
         }
     }
@@ -115,16 +137,16 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
         for (int j = 0; j < N_IN; ++j) Rj[j] = make_float2(pose.R[0][j], pose.R[1][j]);
         const float2 neg_origin = make_float2(-pose.origin[0], -pose.origin[1]);   // proj - origin == proj + (-origin)
         const float2 scale2 = make_float2(grid.scale[0], grid.scale[1]);
-        const float wq_pose = pose.ow * qscale;
-        const float magic_hi = kMagic;
+        const float wq_pose = wq_den;
+        const uint32_t tile_s = smem_u32(tile_u);           // 32-bit shared address: no generic-pointer conversion per add
         unsigned mass32 = 0;
         int wq_count = 0;                                   // warp-uniform
 
-        // quantised add of one corner into the tile
+        // quantised add of one corner into the tile: the subnormal product's bit pattern is the integer
         auto tile_add = [&](int off, float v_times_q) {
-            const int qv = __float_as_int(v_times_q + magic_hi) - kMagicBits;
-            atomicAdd(tile_u + off, (unsigned)qv);
-            mass32 += (unsigned)qv;
+            const uint32_t qv = __float_as_uint(v_times_q);
+            red_shared_u32(tile_s + (uint32_t)off * 4u, qv);
+            mass32 += qv;
         };
         // generic (any position) handling of one point: used for the deferred lanes
         auto slow_point = [&](int p) {
@@ -135,6 +157,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
             if (!stencil(x, pose, grid, i0, dl)) return;
             const float pw = HAS_PW ? __ldg(point_weight + p) : 1.f;
             const float weight = pose.ow * pw;
+            const float wqd = HAS_PW ? wq_den * (pw * pw_scale) : wq_den;
             const float du0 = 1.f - dl[0], du1 = 1.f - dl[1];
             const float w[4] = {du0 * du1, dl[0] * du1, du0 * dl[1], dl[0] * dl[1]};
             const bool x_lo = i0[0] >= 0, x_hi = i0[0] + 1 < g0;
@@ -144,8 +167,8 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                 if (iy < 0 || iy >= g1) continue;
                 if (iy >= ys && iy < ye) {
                     const int off = (iy - ys) * pitch + i0[0];
-                    if (x_lo) tile_add(off, (w[2 * cy] * weight) * qscale);
-                    if (x_hi) tile_add(off + 1, (w[2 * cy + 1] * weight) * qscale);
+                    if (x_lo) tile_add(off, w[2 * cy] * wqd);
+                    if (x_hi) tile_add(off + 1, w[2 * cy + 1] * wqd);
                 } else if (do_border && (iy < tp.band_lo || iy >= tp.band_hi)) {
                     float* addr = img + (int64_t)iy * g0 + i0[0];
                     const float va = w[2 * cy] * weight, vb = w[2 * cy + 1] * weight;
@@ -235,7 +258,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
                     const float2 dl = make_float2(__fsub_rn(coord.x, t.x), __fsub_rn(coord.y, t.y));
                     const float2 du = __fadd2_rn(make_float2(1.f, 1.f), make_float2(-dl.x, -dl.y));
                     const int ix = __float2int_rn(r.x) - 1, iy = __float2int_rn(r.y) - 1;
-                    const float wq = HAS_PW ? wq_pose * pw : wq_pose;
+                    const float wq = HAS_PW ? wq_pose * (pw * pw_scale) : wq_pose;
                     const float a = du.y * wq, bq = dl.y * wq;
                     const int off = (iy - ys) * pitch + ix;
                     tile_add(off, du.x * a);
@@ -297,7 +320,7 @@ fwd_tile2d_fast_kernel(const float* __restrict__ points, const float* __restrict
             const int ry = iy - ys;
             const bool interior = active && (unsigned)ix < (unsigned)(g0 - 1) && (unsigned)ry < (unsigned)(nrows - 1);
             if (interior) {
-                const float wq = HAS_PW ? wq_pose * pw : wq_pose;
+                const float wq = HAS_PW ? wq_pose * (pw * pw_scale) : wq_pose;
                 const float a = du.y * wq, bq = dl.y * wq;
                 const int off = ry * pitch + ix;
                 tile_add(off, du.x * a);

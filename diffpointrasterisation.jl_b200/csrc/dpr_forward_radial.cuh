@@ -63,15 +63,6 @@ __device__ __forceinline__ float point_radius(const float* __restrict__ points, 
     for (int j = 0; j < N_IN; ++j) { x[j] = __ldg(points + p * N_IN + j); r2 = fmaf(x[j], x[j], r2); }
     return sqrtf(r2);
 }
-// Point weights are stored in the packed copy as pw * 2^-em with 2^em >= max(point_weight), i.e. in [0, 1]: the
-// fixed-point scale of a pose then only depends on out_weight (see the kernel).  Power-of-two scaling is exact.
-__device__ __forceinline__ int point_weight_exponent(const float* __restrict__ pw_stats) {
-    if (!pw_stats) return 0;
-    const float wmax = __ldg(pw_stats);
-    int em = 0;
-    if (wmax > 0.f && wmax < 3e38f) frexpf(wmax, &em);
-    return em;
-}
 __device__ __forceinline__ uint32_t radial_key(float r) {
     // NaN compares false -> last bin
     return (r < kRadialMax) ? (uint32_t)(r * ((float)(kRadialBins - 1) / kRadialMax)) : (uint32_t)(kRadialBins - 1);
@@ -147,12 +138,6 @@ static int radial_sort_points(const float* points, const float* point_weight, co
     }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
-}
-
-// shared-memory reduction without return value on a 32-bit shared address (ATOMS.ADD RZ): keeps the address
-// arithmetic in 32 bits and out of the generic-pointer conversion the compiler otherwise repeats per iteration
-__device__ __forceinline__ void red_shared_u32(uint32_t addr, uint32_t v) {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
 }
 
 // streaming 16-byte load that does not allocate in L1: the packed points are read once per CTA, and an L1 fill costs
