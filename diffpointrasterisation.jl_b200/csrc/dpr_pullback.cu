@@ -385,9 +385,14 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
             a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
         return DPR_OK;
     };
-    // paired 8-byte loads need 8-byte aligned rows
+    // Paired 8-byte loads (8-byte aligned rows) pay off only for UNSORTED points, where the 32 lanes of a gather hit 32
+    // unrelated lines (config 2 unsorted: 2.94 ms against 3.24 ms with scalar loads).  With spatially sorted points the
+    // lanes share lines and four 4-byte loads are cheaper for the L1 data stage than an 8-byte load per row plus a
+    // 4-byte load on the odd lanes: config 2 2.11 -> 1.90 ms, config 4 4.20 -> 3.33 ms (profiles/probe_layout_r01.json
+    // shows the same ordering in isolation).  pullback_algo 2 / 3 force pairs / scalars.
+    const int64_t palgo = tuning().pullback_algo;
     const bool pair = sizeof(T) == 4 && (a.grid[0] % 2) == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 8) == 0 &&
-                      tuning().pullback_algo != 3;
+                      palgo != 3 && (palgo == 2 || perm == nullptr);
     if (pair) rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true, true>) : launch(pullback_gather2d_kernel<T, N_IN, K, false, true>);
     else rc = a.point_weight ? launch(pullback_gather2d_kernel<T, N_IN, K, true, false>) : launch(pullback_gather2d_kernel<T, N_IN, K, false, false>);
     if (rc != DPR_OK) return rc;
@@ -566,14 +571,12 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
             a.P < (int64_t)0x3fffffff && a.B < (int64_t)0x7fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff &&
             tuning().point_sort != 2 && a.workspace && a.workspace_bytes >= win_workspace_bytes(a.n_in, a.P) &&
             win_band_rows(dev, a.grid[0], a.grid[1], 3, a.n_in) > 0) {
-            // Worth it when the band covers the projected blob of a CTA's point run: a run of ppc sorted points out of
-            // P spans about g1 * (ppc / P)^(1/n_in) rows.  Measured on B200: config 4 (1 M points, 2-d, 512^2: 32-row
+            // Measured on B200 against the L1-gather kernel WITH PAIRED LOADS: config 4 (1 M points, 2-d, 512^2: 32-row
             // blobs, 54-row bands) 4.23 -> 3.58 ms; config 2 (100 k points, 3-d, 256^2: 86-row blobs, 108-row bands)
-            // 2.12 -> 2.57 ms, so sparse clouds stay on the L1-gather kernel.
-            const double blob_rows = (double)a.grid[1] * pow((double)kTmaConsumers * kWinK / (double)a.P, 1.0 / a.n_in);
-            const bool worth = algo == 5 || (a.P >= 4 * (int64_t)kTmaConsumers * kWinK && a.B >= 64 &&
-                                             a.grid[0] * a.grid[1] * 4 > (int64_t)96 * 1024 &&
-                                             (double)win_band_rows(dev, a.grid[0], a.grid[1], 2, a.n_in) >= 1.5 * blob_rows);
+            // 2.12 -> 2.57 ms.
+            // (second half of the session: with scalar corner loads the L1-gather kernel takes config 4 in 3.33 ms, so
+            // the band kernel is no longer selected automatically; it stays available as pullback_algo 5.)
+            const bool worth = algo == 5;
             if (worth && a.P > 0 && a.B > 0) {
                 return a.n_in == 2 ? pullback_win2d<2>(a, dev) : pullback_win2d<3>(a, dev);
             }
