@@ -25,7 +25,9 @@ __global__ void __launch_bounds__(256) k_gather(const float* __restrict__ img, c
         if (MODE == 0) { g00 = __ldg(img + base); g10 = __ldg(img + base + 1); g01 = __ldg(img + base + G); g11 = __ldg(img + base + G + 1); }
         else if (MODE == 1) { g00 = ld_ca(img + base); g10 = ld_ca(img + base + 1); g01 = ld_ca(img + base + G); g11 = ld_ca(img + base + G + 1); }
         else if (MODE == 2) { g00 = ld_cg(img + base); g10 = ld_cg(img + base + 1); g01 = ld_cg(img + base + G); g11 = ld_cg(img + base + G + 1); }
-        else { g00 = tex1Dfetch<float>(tex, (int)base); g10 = tex1Dfetch<float>(tex, (int)base + 1); g01 = tex1Dfetch<float>(tex, (int)base + G); g11 = tex1Dfetch<float>(tex, (int)base + G + 1); }
+        else if (MODE == 3) { g00 = tex1Dfetch<float>(tex, (int)base); g10 = tex1Dfetch<float>(tex, (int)base + 1); g01 = tex1Dfetch<float>(tex, (int)base + G); g11 = tex1Dfetch<float>(tex, (int)base + G + 1); }
+        else if (MODE == 4) { g00 = __ldg(img + base); g10 = __ldg(img + base + 1); g01 = __ldg(img + base + G); g11 = tex1Dfetch<float>(tex, (int)base + G + 1); }   // 3 LSU + 1 TEX
+        else { g00 = __ldg(img + base); g10 = __ldg(img + base + 1); g01 = tex1Dfetch<float>(tex, (int)base + G); g11 = tex1Dfetch<float>(tex, (int)base + G + 1); }   // 2 LSU + 2 TEX
         acc += g00 * w + g10 * (1.f - w) + g01 * w + g11;
     }
     if (acc == 123.456f) sink[0] = acc;
@@ -54,14 +56,16 @@ int main() {
     cudaTextureObject_t tex = 0; CK(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
     printf("{\"device\": \"%s\", \"results\": [\n", p.name);
     const int ctas = p.multiProcessorCount * 8;
-    const char* names[4] = {"ldg_nc", "ld_ca", "ld_cg", "tex1Dfetch"};
+    const char* names[6] = {"ldg_nc", "ld_ca", "ld_cg", "tex1Dfetch", "3ldg_1tex", "2ldg_2tex"};
     for (int blob : {255, 26, 8}) {
-        for (int mode = 0; mode < 4; ++mode) {
+        for (int mode = 0; mode < 6; ++mode) {
             double ms = 0;
             if (mode == 0) ms = time_ms([&] { k_gather<0><<<ctas, 256>>>(img, tex, sink, G, n_img, iters, blob); }, 3);
             if (mode == 1) ms = time_ms([&] { k_gather<1><<<ctas, 256>>>(img, tex, sink, G, n_img, iters, blob); }, 3);
             if (mode == 2) ms = time_ms([&] { k_gather<2><<<ctas, 256>>>(img, tex, sink, G, n_img, iters, blob); }, 3);
             if (mode == 3) ms = time_ms([&] { k_gather<3><<<ctas, 256>>>(img, tex, sink, G, n_img, iters, blob); }, 3);
+            if (mode == 4) ms = time_ms([&] { k_gather<4><<<ctas, 256>>>(img, tex, sink, G, n_img, iters, blob); }, 3);
+            if (mode == 5) ms = time_ms([&] { k_gather<5><<<ctas, 256>>>(img, tex, sink, G, n_img, iters, blob); }, 3);
             printf(" {\"path\": \"%s\", \"blob\": %d, \"ms\": %.4f, \"corner_loads_per_s\": %.4e},\n", names[mode], blob, ms, (double)ctas * 256 * iters * 4 / (ms * 1e-3));
             fflush(stdout);
         }
