@@ -1,4 +1,5 @@
-// dpr_sort.cuh - spatial binning of the point cloud (counting sort by Morton code of the point's own coordinates).
+// dpr_sort.cuh - spatial binning of the point cloud (counting sort by the Hilbert index - Z-order for 1 bit per
+// dimension - of the cell that holds the point).
 //
 // The pullback gathers ds_dout at the projected position of every point.  With points in their given (arbitrary)
 // order the 32 lanes of a warp hit 32 unrelated 128-byte lines per gather instruction and the L1 data pipe saturates
@@ -12,6 +13,11 @@
 #include "dpr_internal.h"
 
 namespace dpr {
+
+#ifndef DPR_HILBERT
+#define DPR_HILBERT 1
+#endif
+constexpr bool kUseHilbert = DPR_HILBERT != 0;
 
 __device__ __forceinline__ uint32_t part1by1(uint32_t x) {   // spread the low 16 bits to even positions
     x &= 0x0000ffffu;
@@ -30,6 +36,34 @@ __device__ __forceinline__ uint32_t part1by2(uint32_t x) {   // spread the low 1
     return x;
 }
 
+// Hilbert index of an N-d cell (Skilling's transpose algorithm, "Programming the Hilbert curve", 2004): unlike the
+// Z-order curve it has no jumps, so a run of consecutive keys is a compact blob.  Returns the bits*N-bit index.
+template <int N>
+__device__ __forceinline__ uint32_t hilbert_index(uint32_t (&X)[N], int bits) {
+    const uint32_t M = 1u << (bits - 1);
+    for (uint32_t Q = M; Q > 1; Q >>= 1) {                 // inverse undo
+        const uint32_t P = Q - 1;
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+            if (X[i] & Q) X[0] ^= P;
+            else { const uint32_t t = (X[0] ^ X[i]) & P; X[0] ^= t; X[i] ^= t; }
+        }
+    }
+#pragma unroll
+    for (int i = 1; i < N; ++i) X[i] ^= X[i - 1];         // Gray encode
+    uint32_t t = 0;
+    for (uint32_t Q = M; Q > 1; Q >>= 1)
+        if (X[N - 1] & Q) t ^= Q - 1;
+#pragma unroll
+    for (int i = 0; i < N; ++i) X[i] ^= t;
+    // interleave the transposed form: bit b of X[i] is bit (b * N + (N - 1 - i)) of the index
+    uint32_t h = 0;
+    for (int b = bits - 1; b >= 0; --b)
+#pragma unroll
+        for (int i = 0; i < N; ++i) h = (h << 1) | ((X[i] >> b) & 1u);
+    return h;
+}
+
 template <typename T, int N_IN>
 __device__ __forceinline__ uint32_t morton_key(const T* __restrict__ points, int64_t p, int bits) {
     uint32_t q[N_IN];
@@ -42,6 +76,7 @@ __device__ __forceinline__ uint32_t morton_key(const T* __restrict__ points, int
         q[j] = (uint32_t)c;
     }
     if constexpr (N_IN == 1) return q[0];
+    else if (bits >= 2 && kUseHilbert) return hilbert_index<N_IN>(q, bits);
     else if constexpr (N_IN == 2) return part1by1(q[0]) | (part1by1(q[1]) << 1);
     else return part1by2(q[0]) | (part1by2(q[1]) << 1) | (part1by2(q[2]) << 2);
 }
