@@ -4,7 +4,7 @@
 // The pullback gathers ds_dout at the projected position of every point.  With points in their given (arbitrary)
 // order the 32 lanes of a warp hit 32 unrelated 128-byte lines per gather instruction and the L1 data pipe saturates
 // (profiles/: 88 % busy, issue slots 52 %).  A rigid pose maps points that are close in space to pixels that are
-// close in the image, for EVERY pose, so sorting the points once per call along a Z-order curve makes the lanes of a
+// close in the image, for EVERY pose, so sorting the points once per call along a space-filling curve makes the lanes of a
 // warp land in a small blob of each pose image and share cache lines.  The sort is a three-kernel counting sort
 // (histogram, single-CTA scan, scatter); the order inside a bin is arbitrary.  Gradients are written back through
 // the permutation, so callers never see the reordering.
