@@ -149,6 +149,7 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
             for (int j = 0; j < N_IN; ++j) { R[0][j] = par[2 * j]; R[1][j] = par[2 * j + 1]; }
             const float neg_origin[2] = {par[NR], par[NR + 1]};
             const float ow = par[NR + 2];
+            const float ows[2] = {ow * scale[0], ow * scale[1]};
             const float* __restrict__ tile = reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s);
             mbar_wait(&full[s], (i / STAGES) & 1);
 
@@ -169,14 +170,11 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
                 if (x_hi && y_lo) G10 = tile[off + 1];
                 if (x_lo && y_hi) G01 = tile[off + g[0]];
                 if (x_hi && y_hi) G11 = tile[off + g[0] + 1];
-                const float du0 = 1.f - dl[0], du1 = 1.f - dl[1];
-                const float s_ = du1 * (du0 * G00 + dl[0] * G10) + dl[1] * (du0 * G01 + dl[0] * G11);
-                const float gx = du1 * (G10 - G00) + dl[1] * (G11 - G01);
-                const float gy = du0 * (G01 - G00) + dl[0] * (G11 - G10);
+                float s_, gx, gy;
+                bilinear_with_gradient(G00, G10, G01, G11, dl[0], dl[1], s_, gx, gy);
                 acc_ow += HAS_PW ? s_ * pw[k] : s_;
                 dpw[k] += s_ * ow;
-                const float f = HAS_PW ? ow * pw[k] : ow;
-                const float sx = (f * gx) * scale[0], sy = (f * gy) * scale[1];
+                const float sx = gx * (HAS_PW ? ows[0] * pw[k] : ows[0]), sy = gy * (HAS_PW ? ows[1] * pw[k] : ows[1]);
                 if constexpr (N_IN == 3) { acc[6] += sx; acc[7] += sy; } else { acc[4] += sx; acc[5] += sy; }
 #pragma unroll
                 for (int j = 0; j < N_IN; ++j) {
