@@ -231,7 +231,7 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
             for (int j = 0; j < N_IN; ++j) {
                 acc[2 * j] += sx * x[k][j];                    // :69
                 acc[2 * j + 1] += sy * x[k][j];
-                dpt[k][j] += R[0][j] * sx + R[1][j] * sy;      // :70-71
+                dpt[k][j] = fma(R[1][j], sy, fma(R[0][j], sx, dpt[k][j]));      // :70-71
             }
         }
         if constexpr (N_IN == 2) acc[6] = acc_ow;              // 7 values fit the butterfly

@@ -180,7 +180,7 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
                 for (int j = 0; j < N_IN; ++j) {
                     acc[2 * j] += sx * x[k][j];
                     acc[2 * j + 1] += sy * x[k][j];
-                    dpt[k][j] += R[0][j] * sx + R[1][j] * sy;
+                    dpt[k][j] = fmaf(R[1][j], sy, fmaf(R[0][j], sx, dpt[k][j]));
                 }
             }
             __syncwarp();
