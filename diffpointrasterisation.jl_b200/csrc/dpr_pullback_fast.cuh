@@ -237,13 +237,17 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
         if constexpr (N_IN == 2) acc[6] = acc_ow;              // 7 values fit the butterfly
         butterfly8(acc, lane);
         if constexpr (N_IN == 3) acc_ow = warp_sum(acc_ow);
-        if ((lane & 3) == 0) {
-            // butterfly slot -> (rotation entries | translation | out_weight) slot of pose_acc
-            const int slot = vsel;   // N_IN==3: 0..5 rotation, 6..7 translation; N_IN==2: 0..3 rot, 4..5 trans, 6 ow
-            if (slot < NV) atomicAdd(&pose_acc[bl * NV + slot], acc[0]);
-        }
-        if constexpr (N_IN == 3) {
-            if (lane == 1) atomicAdd(&pose_acc[bl * NV + NV - 1], acc_ow);
+        {
+            // butterfly slot -> (rotation entries | translation | out_weight) slot of pose_acc, ONE shared-memory
+            // atomicAdd instruction (a CAS loop on sm_100a) for all of them: lanes 0, 4, .. 28 hold slot vsel
+            // (N_IN==3: 0..5 rotation, 6..7 translation; N_IN==2: 0..3 rot, 4..5 trans, 6 ow), lane 1 the 9th value
+            int slot = vsel;
+            T val = acc[0];
+            bool mine = (lane & 3) == 0 && vsel < NV;
+            if constexpr (N_IN == 3) {
+                if (lane == 1) { slot = NV - 1; val = acc_ow; mine = true; }
+            }
+            if (mine) atomicAdd(&pose_acc[bl * NV + slot], val);
         }
     }
 

@@ -237,9 +237,14 @@ pullback_win2d_kernel(const float* __restrict__ ds_dout,
             if constexpr (N_IN == 2) acc[6] = acc_ow;
             butterfly8(acc, lane);
             if constexpr (N_IN == 3) acc_ow = warp_sum(acc_ow);
-            if ((lane & 3) == 0 && vsel < NV) atomicAdd(&pose_acc[bl * NV + vsel], acc[0]);
-            if constexpr (N_IN == 3) {
-                if (lane == 1) atomicAdd(&pose_acc[bl * NV + NV - 1], acc_ow);
+            {   // one shared-memory atomicAdd instruction (a CAS loop) for all nine sums: see dpr_pullback_fast.cuh
+                int slot = vsel;
+                float val = acc[0];
+                bool mine = (lane & 3) == 0 && vsel < NV;
+                if constexpr (N_IN == 3) {
+                    if (lane == 1) { slot = NV - 1; val = acc_ow; mine = true; }
+                }
+                if (mine) atomicAdd(&pose_acc[bl * NV + slot], val);
             }
         }
         named_bar_sync(1, kTmaConsumers);
