@@ -347,9 +347,7 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     }
     int rc = zero_gradients(a);
     if (rc != DPR_OK) return rc;
-    rc = launch_background_sum(a, grid.cells, dev);
-    if (rc != DPR_OK) return rc;
-    if (a.P == 0 || a.B == 0) return DPR_OK;
+    if (a.P == 0 || a.B == 0) return launch_background_sum(a, grid.cells, dev);
     const T* pts = a.points;
     const T* pwt = a.point_weight;
     const int32_t* perm = nullptr;
@@ -376,13 +374,31 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     if (pose_chunk > 512) pose_chunk = 512;
     if (pose_chunk > a.B) pose_chunk = a.B;
     const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
-    if (point_chunks * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
-    const size_t smem = sizeof(T) * (size_t)pose_chunk * (PP + NV);
+    // d_background: a few extra CTAs per pose chunk inside the gather launch (see the kernel) when there is enough
+    // gather work to hide them behind, else the separate pass
+    // (one bg CTA sums whole images, about 3 MB of them - the duration of a gather CTA; large images, where that is only
+    // a few poses, and launches with few gather CTAs keep the separate pass: config 4 lost 1.7 ms with 51 MB per bg CTA)
+    int bg_ctas = 0;
+    const int64_t img_bytes = grid.cells * (int64_t)sizeof(T);
+    if (a.d_background && img_bytes <= ((int64_t)512 << 10) && point_chunks >= 8 && pose_chunk >= 8) {
+        int64_t n = (pose_chunk * img_bytes + ((int64_t)3 << 20) - 1) / ((int64_t)3 << 20);
+        if (n < 1) n = 1;
+        if (n > pose_chunk) n = pose_chunk;
+        if (n * 4 <= point_chunks) bg_ctas = (int)n;
+    }
+    if (!bg_ctas) {
+        rc = launch_background_sum(a, grid.cells, dev);
+        if (rc != DPR_OK) return rc;
+    }
+    if ((point_chunks + bg_ctas) * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
+    size_t smem = sizeof(T) * (size_t)pose_chunk * (PP + NV);
+    if (smem < sizeof(T) * (size_t)(pose_chunk * PP + 8)) smem = sizeof(T) * (size_t)(pose_chunk * PP + 8);
     auto launch = [&](auto kern) -> int {
         LaunchScope scope("pullback_gather2d", a.stream);
-        kern<<<(unsigned)(point_chunks * pose_chunks), threads, smem, a.stream>>>(
+        kern<<<(unsigned)((point_chunks + bg_ctas) * pose_chunks), threads, smem, a.stream>>>(
             a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
-            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
+            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk,
+            a.d_background, bg_ctas);
         return DPR_OK;
     };
     // Paired 8-byte loads (8-byte aligned rows) pay off only for UNSORTED points, where the 32 lanes of a gather hit 32

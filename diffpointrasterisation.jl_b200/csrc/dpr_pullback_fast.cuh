@@ -98,7 +98,7 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
                          const T* __restrict__ point_weight, T* __restrict__ d_points, T* __restrict__ d_rotation,
                          T* __restrict__ d_translation, T* __restrict__ d_out_weight, T* __restrict__ d_point_weight,
                          const int32_t* __restrict__ perm, Grid<T, 2> grid, int P, int64_t B, int point_chunks,
-                         int pose_chunk) {
+                         int pose_chunk, T* __restrict__ d_background, int bg_ctas) {
     constexpr int NR = 2 * N_IN;            // rotation entries
     constexpr int NV = NR + 3;              // + translation (2) + out_weight
     constexpr int PP = (NV + 3) / 4 * 4;    // padded pose-parameter record: R (col-major), -origin (2), ow
@@ -106,10 +106,47 @@ pullback_gather2d_kernel(const T* __restrict__ ds_dout, const T* __restrict__ po
     T* pose_par = reinterpret_cast<T*>(smem_raw);              // [pose_chunk][PP]
     T* pose_acc = pose_par + (size_t)pose_chunk * PP;          // [pose_chunk][NV]
 
-    const int pc = blockIdx.x % point_chunks;
-    const int64_t bc = blockIdx.x / point_chunks;
+    // CTA layout: per pose chunk, point_chunks gather CTAs followed by bg_ctas CTAs that compute d_background of the
+    // chunk's poses (src/raster_pullback.jl:78).  CTAs are dispatched in blockIdx order, so those run while the chunk's
+    // gather CTAs are resident and have pulled the chunk's images into L2, and they use HBM / L2 bandwidth the gather
+    // CTAs (bound by the L1 data pipe) leave idle: the separate 0.17 ms background_sum pass of config 2 disappears.
+    const int per_chunk = point_chunks + bg_ctas;
+    const int pc = blockIdx.x % per_chunk;
+    const int64_t bc = blockIdx.x / per_chunk;
     const int64_t b0 = bc * pose_chunk;
     const int n_pose = (int)((b0 + pose_chunk < B ? b0 + pose_chunk : B) - b0);
+    if (pc >= point_chunks) {
+        const int e = pc - point_chunks;
+        const int per = (n_pose + bg_ctas - 1) / bg_ctas;
+        const int lo = e * per, hi = (lo + per < n_pose) ? lo + per : n_pose;
+        const int64_t cells = grid.cells;
+        const bool vec = sizeof(T) == 4 && (cells & 3) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) & 15) == 0;
+        T* warp_part = pose_acc;                               // 8 partial sums (the dynamic smem holds >= 8 values)
+        for (int bl = lo; bl < hi; ++bl) {
+            const T* __restrict__ src = ds_dout + (b0 + bl) * cells;
+            T acc0 = T(0), acc1 = T(0);
+            if (vec) {
+                const float4* __restrict__ v4 = reinterpret_cast<const float4*>(src);
+                for (int64_t i = threadIdx.x; i < cells / 4; i += blockDim.x) {
+                    const float4 q = __ldg(v4 + i);
+                    acc0 += T(q.x) + T(q.y);
+                    acc1 += T(q.z) + T(q.w);
+                }
+            } else {
+                for (int64_t i = threadIdx.x; i < cells; i += blockDim.x) acc0 += __ldg(src + i);
+            }
+            T t = warp_sum(acc0 + acc1);
+            if ((threadIdx.x & 31) == 0) warp_part[threadIdx.x >> 5] = t;
+            __syncthreads();
+            if (threadIdx.x < 32) {
+                t = threadIdx.x < (blockDim.x >> 5) ? warp_part[threadIdx.x] : T(0);
+                t = warp_sum(t);
+                if (threadIdx.x == 0) d_background[b0 + bl] = t;
+            }
+            __syncthreads();
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < n_pose * PP; i += blockDim.x) {
         const int bl = i / PP, v = i % PP;
         const int64_t b = b0 + bl;
