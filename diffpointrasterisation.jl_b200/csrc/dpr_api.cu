@@ -85,7 +85,7 @@ int current_device_info(DeviceInfo& info) {
 
 static int check_dims(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B) {
     if (!grid) return DPR_ERR_NULL_POINTER;
-    if (n_in < 1 || n_in > 3 || n_out < 1 || n_out > n_in) return DPR_ERR_UNSUPPORTED;   // any N_out <= N_in <= 3
+    if (n_in < 1 || n_in > kMaxDim || n_out < 1 || n_out > kMaxDim) return DPR_ERR_UNSUPPORTED;   // any 1 <= N_in, N_out <= 4
     if (P < 0 || B < 0) return DPR_ERR_BAD_DIMS;
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) {
@@ -111,7 +111,7 @@ static int forward_entry(int n_in, int n_out, const int64_t* grid, int64_t P, in
     if (!workspace || workspace_bytes < 256) return DPR_ERR_WORKSPACE;   // smaller than dpr_workspace_bytes(): no point sort
     ForwardArgs<T> a;
     a.n_in = n_in; a.n_out = n_out;
-    for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
+    for (int k = 0; k < kMaxDim; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
     a.P = P; a.B = B;
     a.points = points; a.rotation = rotation; a.translation = translation;
     a.background = background; a.out_weight = out_weight; a.point_weight = point_weight;
@@ -137,7 +137,7 @@ static int pullback_entry(int n_in, int n_out, const int64_t* grid, int64_t P, i
     if (workspace_bytes < 256) return DPR_ERR_WORKSPACE;   // smaller than dpr_workspace_bytes(): the point sort is skipped
     PullbackArgs<T> a;
     a.n_in = n_in; a.n_out = n_out;
-    for (int k = 0; k < 3; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
+    for (int k = 0; k < kMaxDim; ++k) a.grid[k] = k < n_out ? grid[k] : 1;
     a.P = P; a.B = B;
     a.ds_dout = ds_dout; a.points = points; a.rotation = rotation; a.translation = translation;
     a.out_weight = out_weight; a.point_weight = point_weight;

@@ -611,7 +611,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
 template <typename T>
 int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
     const int64_t algo = tuning().forward_algo;
-    if (a.n_out == 2 && algo != 1 && a.P > 0 && a.B > 0) {
+    if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && algo != 1 && a.P > 0 && a.B > 0) {
         TileParams<T> tp;
         size_t smem = 0;
         bool use_fast = false;
@@ -624,12 +624,12 @@ int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
             if (a.n_in == 3) return forward_tile2d<T, 3>(a, dev, tp, smem);
         }
     }
-    if (a.n_in == 2 && a.n_out == 2) return forward_global<T, 2, 2>(a, dev);
-    if (a.n_in == 3 && a.n_out == 2) return forward_global<T, 3, 2>(a, dev);
-    if (a.n_in == 3 && a.n_out == 3) return forward_global<T, 3, 3>(a, dev);
-    if (a.n_in == 1 && a.n_out == 1) return forward_global<T, 1, 1>(a, dev);
-    if (a.n_in == 2 && a.n_out == 1) return forward_global<T, 2, 1>(a, dev);
-    if (a.n_in == 3 && a.n_out == 1) return forward_global<T, 3, 1>(a, dev);
+    // every (N_in, N_out) up to kMaxDim: the reference generates its kernel for any pair (src/raster.jl:36-66)
+#define DPR_FWD_CASE(NI, NO) if (a.n_in == NI && a.n_out == NO) return forward_global<T, NI, NO>(a, dev);
+#define DPR_FWD_ROW(NI) DPR_FWD_CASE(NI, 1) DPR_FWD_CASE(NI, 2) DPR_FWD_CASE(NI, 3) DPR_FWD_CASE(NI, 4)
+    DPR_FWD_ROW(1) DPR_FWD_ROW(2) DPR_FWD_ROW(3) DPR_FWD_ROW(4)
+#undef DPR_FWD_ROW
+#undef DPR_FWD_CASE
     return DPR_ERR_UNSUPPORTED;
 }
 

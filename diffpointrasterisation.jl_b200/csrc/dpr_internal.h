@@ -47,10 +47,14 @@ void set_error_message(const char* msg);            // thread-local text behind 
         if (e__ != cudaSuccess) return ::dpr::cuda_fail(e__, #expr);    \
     } while (0)
 
+// Largest N_in / N_out the generic kernels are instantiated for (the reference is dimension-generic through generated
+// functions, src/util.jl:26-27; 2^N_out corners per splat make anything beyond 4 output dimensions impractical).
+constexpr int kMaxDim = 4;
+
 template <typename T>
 struct ForwardArgs {
     int n_in, n_out;
-    int64_t grid[3];
+    int64_t grid[kMaxDim];
     int64_t P, B;
     const T *points, *rotation, *translation, *background, *out_weight, *point_weight;
     T* out;
@@ -62,7 +66,7 @@ struct ForwardArgs {
 template <typename T>
 struct PullbackArgs {
     int n_in, n_out;
-    int64_t grid[3];
+    int64_t grid[kMaxDim];
     int64_t P, B;
     const T *ds_dout, *points, *rotation, *translation, *out_weight, *point_weight;
     T *d_points, *d_rotation, *d_translation, *d_background, *d_out_weight, *d_point_weight;

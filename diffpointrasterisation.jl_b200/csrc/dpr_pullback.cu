@@ -233,7 +233,8 @@ static bool use_sort(const PullbackArgs<T>& a) {
 template <typename T, int N_IN, int N_OUT>
 static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     constexpr int NV = PoseGradLayout<N_IN, N_OUT>::NV;
-    constexpr int K = 4;
+    // points owned per thread: 4 for the tuned dimensions, fewer when N_in * N_out values per point would spill
+    constexpr int K = (N_IN <= 3 && N_OUT <= 3) ? 4 : ((N_IN == 4 && N_OUT == 4) ? 1 : 2);
     Grid<T, N_OUT> grid;
     grid.cells = 1;
     for (int k = 0; k < N_OUT; ++k) {
@@ -570,7 +571,7 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
         // TMA-staged kernel: whole pose image on chip, 16-byte aligned images, enough points to fill the CTAs
         const int64_t cells2 = a.n_out == 2 ? a.grid[0] * a.grid[1] : 0;
         const int64_t algo = tuning().pullback_algo;
-        if (a.n_out == 2 && (algo == 0 || algo == 4) && cells2 > 0 && (cells2 % 4) == 0 &&
+        if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && (algo == 0 || algo == 4) && cells2 > 0 && (cells2 % 4) == 0 &&
             (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && a.P < (int64_t)0x3fffffff) {
             int stages = 0;
             if (tma_pullback_smem(cells2, 3, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 3;
@@ -602,12 +603,12 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
         if (a.n_in == 2) return pullback_gather2d<T, 2>(a, dev);
         if (a.n_in == 3) return pullback_gather2d<T, 3>(a, dev);
     }
-    if (a.n_in == 2 && a.n_out == 2) return pullback_global<T, 2, 2>(a, dev);
-    if (a.n_in == 3 && a.n_out == 2) return pullback_global<T, 3, 2>(a, dev);
-    if (a.n_in == 3 && a.n_out == 3) return pullback_global<T, 3, 3>(a, dev);
-    if (a.n_in == 1 && a.n_out == 1) return pullback_global<T, 1, 1>(a, dev);
-    if (a.n_in == 2 && a.n_out == 1) return pullback_global<T, 2, 1>(a, dev);
-    if (a.n_in == 3 && a.n_out == 1) return pullback_global<T, 3, 1>(a, dev);
+    // every (N_in, N_out) up to kMaxDim, like the reference's generated pullback (src/raster_pullback.jl:2-82)
+#define DPR_PB_CASE(NI, NO) if (a.n_in == NI && a.n_out == NO) return pullback_global<T, NI, NO>(a, dev);
+#define DPR_PB_ROW(NI) DPR_PB_CASE(NI, 1) DPR_PB_CASE(NI, 2) DPR_PB_CASE(NI, 3) DPR_PB_CASE(NI, 4)
+    DPR_PB_ROW(1) DPR_PB_ROW(2) DPR_PB_ROW(3) DPR_PB_ROW(4)
+#undef DPR_PB_ROW
+#undef DPR_PB_CASE
     return DPR_ERR_UNSUPPORTED;
 }
 

@@ -17,7 +17,8 @@
  * then accumulates: ext/DiffPointRasterisationCUDAExt.jl:272-276; forward overwrites with the background,
  * src/raster.jl:27), so callers need not pre-zero.  All work is enqueued on `stream`; nothing synchronises.
  *
- * Supported: T in {float, double}; any 1 <= N_out <= N_in <= 3 (tuned kernels for the 2-d outputs (2,2) and (3,2)).
+ * Supported: T in {float, double}; any 1 <= N_in <= 4, 1 <= N_out <= 4 (the reference generates its kernels for any pair,
+ * src/raster.jl:36-66, src/util.jl:26-27); tuned kernels for the 2-d outputs (2,2) and (3,2), generic ones elsewhere.
  * Return value: DPR_OK (0) or a negative dpr_status; never throws, never aborts.
  */
 #ifndef DPR_H
@@ -35,7 +36,7 @@ typedef void* dpr_stream_t; /* cudaStream_t / CUstream (CUDA.jl: stream().handle
 enum dpr_status {
     DPR_OK = 0,
     DPR_ERR_BAD_DIMS = -1,      /* negative sizes, grid extent < 1, prod(grid)*B overflow            */
-    DPR_ERR_UNSUPPORTED = -2,   /* (N_in, N_out) or element size outside the supported set            */
+    DPR_ERR_UNSUPPORTED = -2,   /* N_in or N_out outside 1..4, or element size outside the supported set */
     DPR_ERR_NULL_POINTER = -3,  /* a required pointer is NULL                                          */
     DPR_ERR_WORKSPACE = -4,     /* workspace smaller than dpr_workspace_bytes()                        */
     DPR_ERR_CUDA = -5,          /* a CUDA runtime call failed; see dpr_last_error_message()            */

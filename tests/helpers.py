@@ -17,13 +17,14 @@ def golden_forward_args(case, dtype=np.float64):
 def random_rotations(rng, n_in, n_out, B, dtype):
     """Haar-uniform rotations (test/data.jl:29-31); projections keep the first n_out rows (P*R, :13-16,:42-44)."""
     out = np.empty((n_out, n_in, B), dtype=dtype, order="F")
+    n = max(n_in, n_out)                     # n_out > n_in (an embedding): the first n_in columns of a rotation
     for b in range(B):
-        a = rng.standard_normal((n_in, n_in))
+        a = rng.standard_normal((n, n))
         q, r = np.linalg.qr(a)
         q = q * np.sign(np.diag(r))
-        if n_in > 1 and np.linalg.det(q) < 0:
+        if n > 1 and np.linalg.det(q) < 0:
             q[:, 0] = -q[:, 0]
-        out[:, :, b] = q[:n_out, :]
+        out[:, :, b] = q[:n_out, :n_in]
     return out
 
 

@@ -85,8 +85,13 @@ def test_argument_validation_without_gpu():
     lib = _lib.load()
     grid = (ctypes.c_int64 * 2)(8, 8)
     f = lib.dpr_raster_forward_f32
-    assert f(4, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2   # unsupported dims
-    assert f(2, 3, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2   # N_out > N_in
+    assert f(5, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2   # unsupported dims
+    assert f(2, 5, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2
+    assert f(0, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -2
+    for n_in in range(1, 5):                 # every pair up to 4 x 4 passes the dimension check (NULL pointers next)
+        for n_out in range(1, 5):
+            g4 = (ctypes.c_int64 * 4)(8, 8, 8, 8)
+            assert f(n_in, n_out, g4, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -3
     assert f(3, 2, grid, -1, 1, None, None, None, None, None, None, None, None, 0, None) == -1  # bad dims
     assert f(3, 2, (ctypes.c_int64 * 2)(0, 8), 1, 1, None, None, None, None, None, None, None, None, 0, None) == -1
     assert f(3, 2, grid, 1, 1, None, None, None, None, None, None, None, None, 0, None) == -3   # NULL pointers

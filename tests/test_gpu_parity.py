@@ -80,6 +80,41 @@ def test_parity_random(dtype, n_in, n_out, grid, weights):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n_in,n_out,grid", [(4, 2, (40, 24)), (4, 3, (12, 10, 8)), (4, 4, (7, 6, 5, 8)), (4, 1, (33,)),
+                                             (3, 4, (6, 5, 4, 7)), (2, 4, (5, 6, 7, 4)), (1, 4, (4, 5, 3, 6)),
+                                             (2, 3, (10, 12, 9)), (1, 3, (8, 6, 7)), (1, 2, (16, 12))])
+@pytest.mark.parametrize("weights", [True, False])
+def test_parity_generic_dimensions(dtype, n_in, n_out, grid, weights):
+    """The reference generates raster / raster_pullback! for any (N_in, N_out) (src/raster.jl:36-66, src/util.jl:26-27,
+    README.md:13 "arbitrary-dimensional"); the library instantiates every pair up to 4 x 4, projections and embeddings."""
+    d = make_inputs(300 + n_in * 10 + n_out, n_in, n_out, 6007, 7, grid, dtype, weights)
+    _check(d, grid, dtype, f"{n_in}->{n_out} {grid}")
+    with forced(point_sort=1, pose_chunk=3):              # the spatially sorted copy of 1-d ... 4-d points
+        _check(d, grid, dtype, f"{n_in}->{n_out} {grid} sorted")
+
+
+def test_generic_dimensions_batched_equals_singles_and_empty():
+    """4-d -> 4-d: the batch is a set of independent poses (src/raster.jl:383-431), empty clouds give the background."""
+    grid = (6, 5, 7, 4)
+    d = make_inputs(77, 4, 4, 501, 5, grid, np.float64)
+    args = dev_args(d, np.float64)
+    ds = to_dev(d["ds_dout"])
+    out = dpr_b200.raster(grid, *args)
+    pb = dpr_b200.raster_pullback_(ds, *args)
+    acc = torch.zeros_like(pb.points)
+    for b in range(5):
+        sl = lambda t: dpr_b200.fortran(t[..., b:b + 1])
+        one = (args[0], sl(args[1]), sl(args[2]), args[3][b:b + 1], args[4][b:b + 1], args[5])
+        assert rel_l2(to_np(dpr_b200.raster(grid, *one)[..., 0]), to_np(out[..., b])) < 1e-13
+        pb1 = dpr_b200.raster_pullback_(sl(ds), *one)
+        assert rel_l2(to_np(pb1.rotation[..., 0]), to_np(pb.rotation[..., b])) < 1e-12
+        acc += pb1.points
+    assert rel_l2(to_np(acc), to_np(pb.points)) < 1e-12
+    empty = dpr_b200.raster(grid, dpr_b200.empty_f((4, 0), torch.float64, "cuda"), args[1], args[2], args[3], args[4], None)
+    assert torch.equal(empty, args[3].reshape(1, 1, 1, 1, 5).expand(*grid, 5))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("algo,opts", [(1, {}), (2, {}), (2, dict(tile_smem_bytes=48 * 48 * 8)), (2, dict(tile_smem_bytes=13 * 48 * 8)),
                                        (2, dict(point_split=3)), (2, dict(point_split=3, tile_smem_bytes=40 * 48 * 8))])
 def test_forward_paths_agree(dtype, algo, opts):

@@ -70,7 +70,8 @@ def test_readme_ds_dout_is_consistent_with_forward(golden):
     np.testing.assert_allclose(2 * (np.asarray(g["target_image"]) - out), np.asarray(g["ds_dout"]), atol=2e-5)
 
 
-@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (8, 8)), (3, 3, (8, 8, 8)), (2, 2, (16, 12)), (3, 1, (9,))])
+@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (8, 8)), (3, 3, (8, 8, 8)), (2, 2, (16, 12)), (3, 1, (9,)),
+                                             (4, 4, (5, 4, 6, 3)), (4, 2, (8, 8)), (2, 3, (6, 7, 5)), (1, 4, (3, 4, 5, 6))])
 @pytest.mark.parametrize("weights", [True, False])
 def test_c_oracle_matches_numpy_restatement(n_in, n_out, grid, weights):
     d = make_inputs(7, n_in, n_out, 300, 5, grid, np.float64, weights)
@@ -106,7 +107,7 @@ def test_batched_equals_singles_and_thread_invariance(n_in, n_out, grid):
     assert rel_l2(pb.points, d_points) < 1e-13 and rel_l2(pb.point_weight, d_pw) < 1e-13
 
 
-@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (8, 8)), (3, 3, (8, 8, 8))])
+@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (8, 8)), (3, 3, (8, 8, 8)), (4, 4, (5, 4, 6, 3)), (2, 3, (6, 7, 5))])
 def test_pullback_is_gradient_of_forward_finite_differences(n_in, n_out, grid):
     """<ds_dout, raster(args)> differentiated numerically (test/chainrules.jl:6-89 does this with test_rrule)."""
     d = make_inputs(3, n_in, n_out, 12, 3, grid, np.float64)
