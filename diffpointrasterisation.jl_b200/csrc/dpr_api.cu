@@ -393,7 +393,7 @@ const char* dpr_status_string(int status) {
     switch (status) {
         case DPR_OK: return "ok";
         case DPR_ERR_BAD_DIMS: return "bad dimensions (negative size, grid extent < 1, or size overflow)";
-        case DPR_ERR_UNSUPPORTED: return "unsupported (N_in, N_out) or element type; supported: 1 <= N_out <= N_in <= 3 in f32/f64";
+        case DPR_ERR_UNSUPPORTED: return "unsupported (N_in, N_out) or element type; supported: 1 <= N_in <= 4, 1 <= N_out <= 4 in f32/f64";
         case DPR_ERR_NULL_POINTER: return "a required pointer is NULL";
         case DPR_ERR_WORKSPACE: return "workspace smaller than dpr_workspace_bytes()";
         case DPR_ERR_CUDA: return "CUDA runtime error (see dpr_last_error_message)";
@@ -407,6 +407,8 @@ const char* dpr_status_string(int status) {
 const char* dpr_last_error_message(void) { return tl_error; }
 
 size_t dpr_workspace_bytes(int op, int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, int sizeof_T) {
+    // arguments the entry points would reject anyway: no scratch (and no division by n_in = 0 in the sort plan)
+    if (n_in < 1 || n_in > kMaxDim || n_out < 1 || n_out > kMaxDim || P < 0 || B < 0 || (sizeof_T != 4 && sizeof_T != 8)) return 0;
     if (op == DPR_OP_FORWARD) return forward_workspace_bytes(n_in, n_out, grid, P, B, sizeof_T);
     if (op == DPR_OP_PULLBACK) return pullback_workspace_bytes(n_in, n_out, grid, P, B, sizeof_T);
     return 0;

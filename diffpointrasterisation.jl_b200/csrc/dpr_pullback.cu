@@ -275,6 +275,9 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
         if (pose_chunk < 8) pose_chunk = a.B < 8 ? a.B : 8;
     }
     if (pose_chunk > 512) pose_chunk = 512;
+    // the per-pose accumulators must fit the 48 KB of dynamic shared memory a kernel gets without opting in
+    // (Float64 with N_in * N_out >= 9: 512 poses would need 53 - 86 KB and the launch would fail)
+    if (pose_chunk > (int64_t)(48 * 1024 / (sizeof(T) * NV))) pose_chunk = (int64_t)(48 * 1024 / (sizeof(T) * NV));
     if (pose_chunk > a.B) pose_chunk = a.B;
     const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
     if (point_chunks * pose_chunks > (int64_t)0x7fffffff || point_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
@@ -373,6 +376,9 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
         if (pose_chunk < 8) pose_chunk = a.B < 8 ? a.B : 8;
     }
     if (pose_chunk > 512) pose_chunk = 512;
+    // pose records + accumulators must fit the 48 KB of dynamic shared memory a kernel gets without opting in
+    // (Float64, 3-d points: 512 poses would need 86 KB and the launch would fail)
+    if (pose_chunk > (int64_t)(48 * 1024 / (sizeof(T) * (PP + NV)))) pose_chunk = (int64_t)(48 * 1024 / (sizeof(T) * (PP + NV)));
     if (pose_chunk > a.B) pose_chunk = a.B;
     const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
     // d_background: a few extra CTAs per pose chunk inside the gather launch (see the kernel) when there is enough

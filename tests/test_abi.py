@@ -78,6 +78,8 @@ def test_status_strings_and_options():
     assert _lib.get_option(_lib.OPT_FORWARD_ALGO) == 1
     _lib.set_option(_lib.OPT_FORWARD_ALGO, 0)
     assert lib.dpr_workspace_bytes(0, 3, 2, (ctypes.c_int64 * 2)(8, 8), 10, 2, 4) <= 4096
+    for bad in ((0, 2, 10, 2, 4), (3, 0, 10, 2, 4), (5, 2, 10, 2, 4), (3, 2, -1, 2, 4), (3, 2, 10, 2, 2)):   # never traps
+        assert lib.dpr_workspace_bytes(1, bad[0], bad[1], (ctypes.c_int64 * 2)(8, 8), bad[2], bad[3], bad[4]) == 0
 
 
 def test_argument_validation_without_gpu():

@@ -331,6 +331,15 @@ def test_pullback_pose_chunking(pose_chunk, algo):
         assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-10, k
 
 
+@pytest.mark.parametrize("n_in,n_out,grid", [(3, 2, (16, 12)), (2, 2, (16, 12)), (3, 3, (6, 5, 7)), (4, 4, (4, 3, 5, 4))])
+def test_pullback_float64_pose_chunk_fits_default_shared_memory(n_in, n_out, grid):
+    """Float64 pose records + accumulators of 500 poses exceed the 48 KB a launch gets without opting in (e.g. 3-d points:
+    8 B x 21 values x 500 = 84 KB); the library must shrink the chunk instead of failing the launch."""
+    d = make_inputs(515, n_in, n_out, 3001, 520, grid, np.float64)
+    with forced(pose_chunk=500):
+        _check(d, grid, np.float64, f"{n_in}->{n_out} 520 poses, chunk 500")
+
+
 @pytest.mark.parametrize("n_in", [2, 3])
 @pytest.mark.parametrize("weights", [True, False])
 @pytest.mark.parametrize("B,pose_chunk", [(5, 0), (150, 0), (150, 70)])
