@@ -243,6 +243,11 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
     if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
     DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
     int64_t chunk = 0;
+    // never return (DPR_CUDA_TRY) with copies into the caller's buffers still in flight
+    struct Drain {
+        HostArena* ar;
+        ~Drain() { for (int i = 0; i < NSTREAM; ++i) cudaStreamSynchronize(ar->streams[i]); }
+    } drain{ar};
     for (int64_t b0 = 0; b0 < B; b0 += cb, ++chunk) {
         const int64_t nb = (b0 + cb < B) ? cb : B - b0;
         const int si = (int)(chunk % NSTREAM);
@@ -323,7 +328,16 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
     DPR_CUDA_TRY(cudaMemsetAsync(tot_dp, 0, grad_bytes, s0));
     DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
     int64_t chunk = 0;
-    cudaEvent_t done[NSTREAM] = {nullptr, nullptr, nullptr};
+    // events are destroyed and the streams drained on every exit path, including the early returns of DPR_CUDA_TRY
+    struct Cleanup {
+        HostArena* ar;
+        cudaEvent_t done[NSTREAM] = {nullptr, nullptr, nullptr};
+        ~Cleanup() {
+            for (int i = 0; i < NSTREAM; ++i) cudaStreamSynchronize(ar->streams[i]);
+            for (int i = 0; i < NSTREAM; ++i) if (done[i]) cudaEventDestroy(done[i]);
+        }
+    } cleanup{ar};
+    cudaEvent_t (&done)[NSTREAM] = cleanup.done;
     for (int64_t b0 = 0; b0 < B && rc == DPR_OK; b0 += cb, ++chunk) {
         const int64_t nb = (b0 + cb < B) ? cb : B - b0;
         const int si = (int)(chunk % NSTREAM);
@@ -377,7 +391,6 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
     }
     cudaError_t e = cudaStreamSynchronize(s0);
     if (e != cudaSuccess && rc == DPR_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
-    for (int i = 0; i < NSTREAM; ++i) if (done[i]) cudaEventDestroy(done[i]);
     return rc;
 }
 

@@ -13,10 +13,14 @@ CASES = [("cfg1 (full size)", 3, 2, 10000, 64, (128, 128), np.float64, False),
          ("cfg2 (100k points, 16 of 4096 poses)", 3, 2, 100000, 16, (256, 256), np.float32, False),
          ("cfg3 (1M points, 2 of 16 poses, 128^3)", 3, 3, 1000000, 2, (128, 128, 128), np.float32, False),
          ("cfg4 (1M points, 4 of 1024 poses)", 2, 2, 1000000, 4, (512, 512), np.float32, True),
-         ("cfg5 (1M points, 32 of 16384 poses)", 3, 2, 1000000, 32, (128, 128), np.float32, False)]
+         ("cfg5 (1M points, 32 of 16384 poses)", 3, 2, 1000000, 32, (128, 128), np.float32, False),
+         # dimension pairs beyond the BASELINE configs (every pair up to 4 x 4 is instantiated; generic kernels)
+         ("4d->4d, 200k points, 4 poses, 24^4", 4, 4, 200000, 4, (24, 24, 24, 24), np.float32, True),
+         ("4d->2d, 200k points, 8 poses, 128^2", 4, 2, 200000, 8, (128, 128), np.float32, False),
+         ("2d->3d (embedding), 200k points, 4 poses, 64^3", 2, 3, 200000, 4, (64, 64, 64), np.float64, True)]
 F = ("points", "rotation", "translation", "background", "out_weight", "point_weight")
 for name, n_in, n_out, P, B, grid, dtype, weights in CASES:
-    d = make_inputs(1000 + int(name[3]), n_in, n_out, P, B, grid, dtype, weights)
+    d = make_inputs(1000 + int(name[3]) if name.startswith("cfg") else 2000 + 10 * n_in + n_out, n_in, n_out, P, B, grid, dtype, weights)
     a = tuple(d[k] for k in F)
     acc = dtype == np.float32
     ref_out = oracle.raster(grid, *a, dtype=dtype, n_threads=8, f64_accumulate=acc)
@@ -24,7 +28,7 @@ for name, n_in, n_out, P, B, grid, dtype, weights in CASES:
     td = torch.float32 if acc else torch.float64
     args = dev_args(d, dtype)
     print(f"== {name}, {'Float32 vs f64-accumulate oracle (gate 1e-5)' if acc else 'Float64 vs faithful oracle (gate 1e-10)'}")
-    if n_out == 2 and acc:
+    if n_out == 2 and n_in in (2, 3) and acc:     # the tile kernels exist for 2-d and 3-d points
         for label, opts in (("fixed-point tile", dict(forward_accum=0)), ("float CAS tile", dict(forward_accum=1)), ("global REDG", dict(forward_algo=1))):
             with forced(**opts):
                 out = dpr_b200.raster(grid, *args)

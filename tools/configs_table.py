@@ -23,7 +23,7 @@ for c in order:
         fwd += rest
     cpu = j.get("cpu_baseline") or {}
     rows.append(f"| {c} | {j['config']['workload'].split(': ', 1)[1]} | {j['ms_per_step']:.3f} | {fwd:.3f} | {bwd:.3f} | {j['value']:.3g} | "
-                f"{100 * j['roofline']['whole_step']['frac']:.1f} % | {cpu.get('value', float('nan')):.3g} ({cpu.get('cores', '?')} cores) | "
+                f"{100 * j['roofline']['whole_step']['frac']:.1f} % | " + (f"{cpu['value']:.3g} ({cpu.get('cores', '?')} cores)" if cpu.get('value') else "not re-run") + " | "
                 f"{j['config']['forward_path']} / {j['config']['pullback_path']} |")
 open(os.path.join(d, "table.md"), "w").write("\n".join(rows) + "\n")
 print("\n".join(rows))
