@@ -171,19 +171,29 @@ function DiffPointRasterisation.raster_pullback!(
     out_weight, point_weight = _materialise(out_weight), _materialise(point_weight)
     grid = collect(Int64, size(ds_dout)[1:N_out])
     ws = _workspace(DPR_OP_PULLBACK, N_in, N_out, grid, n_points, batch_size, T)
-    argtypes = (Cint, Cint, Ptr{Int64}, Int64, Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T},
-                CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid})
-    args = (N_in, N_out, grid, n_points, batch_size, pointer(ds_dout),
-            reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
-            reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, out_weight), _devptr(T, point_weight),
-            pointer(ds_dpoints), pointer(ds_drotation), pointer(ds_dtranslation), pointer(ds_dbackground),
-            pointer(ds_dout_weight), pointer(ds_dpoint_weight), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
-            CUDA.stream().handle)
+    # `ccall` needs its argument types as a literal tuple and takes no splatted arguments, so both element types are
+    # written out (the same 20 arguments as dpr_raster_pullback_f32 / _f64 in include/dpr.h)
     GC.@preserve ds_dout points rotation translation out_weight point_weight ds_dpoints ds_drotation ds_dtranslation ds_dbackground ds_dout_weight ds_dpoint_weight ws begin
         rc = if T === Float32
-            ccall((:dpr_raster_pullback_f32, libdpr), Cint, argtypes, args...)
+            ccall((:dpr_raster_pullback_f32, libdpr), Cint,
+                  (Cint, Cint, Ptr{Int64}, Int64, Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T},
+                   CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                  N_in, N_out, grid, n_points, batch_size, pointer(ds_dout),
+                  reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
+                  reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, out_weight), _devptr(T, point_weight),
+                  pointer(ds_dpoints), pointer(ds_drotation), pointer(ds_dtranslation), pointer(ds_dbackground),
+                  pointer(ds_dout_weight), pointer(ds_dpoint_weight), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
+                  CUDA.stream().handle)
         else
-            ccall((:dpr_raster_pullback_f64, libdpr), Cint, argtypes, args...)
+            ccall((:dpr_raster_pullback_f64, libdpr), Cint,
+                  (Cint, Cint, Ptr{Int64}, Int64, Int64, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T},
+                   CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                  N_in, N_out, grid, n_points, batch_size, pointer(ds_dout),
+                  reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
+                  reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, out_weight), _devptr(T, point_weight),
+                  pointer(ds_dpoints), pointer(ds_drotation), pointer(ds_dtranslation), pointer(ds_dbackground),
+                  pointer(ds_dout_weight), pointer(ds_dpoint_weight), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
+                  CUDA.stream().handle)
         end
         _check(rc)
     end
