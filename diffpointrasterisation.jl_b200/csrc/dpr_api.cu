@@ -514,7 +514,7 @@ int dpr_set_option(int option, int64_t value) {
     if (value < 0) return DPR_ERR_BAD_OPTION;
     switch (option) {
         case DPR_OPT_FORWARD_ALGO: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.forward_algo = value; return DPR_OK;
-        case DPR_OPT_PULLBACK_ALGO: if (value > 5) return DPR_ERR_BAD_OPTION; g_tuning.pullback_algo = value; return DPR_OK;
+        case DPR_OPT_PULLBACK_ALGO: if (value > 6) return DPR_ERR_BAD_OPTION; g_tuning.pullback_algo = value; return DPR_OK;
         case DPR_OPT_TILE_SMEM_BYTES: g_tuning.tile_smem_bytes = value; return DPR_OK;
         case DPR_OPT_POINT_SPLIT: g_tuning.point_split = value; return DPR_OK;
         case DPR_OPT_POSE_CHUNK: g_tuning.pose_chunk = value; return DPR_OK;

@@ -12,6 +12,7 @@
 // CTA as one REDG per (pose, value).  CTAs are ordered so that neighbours work on the same poses at the same time,
 // which keeps the ds_dout images they gather from resident in L1/L2.
 #include <cmath>
+#include <cstdlib>
 
 #include "dpr_common.cuh"
 #include "dpr_internal.h"
@@ -295,6 +296,7 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 
 }  // namespace dpr
 #include "dpr_pullback_fast.cuh"
+#include "dpr_pullback_box.cuh"
 #include "dpr_pullback_tma.cuh"
 #include "dpr_pullback_win.cuh"
 namespace dpr {
@@ -421,6 +423,85 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
     set_last_path(DPR_OP_PULLBACK, perm ? (pair ? "gather2d_pair_sorted" : "gather2d_sorted") : (pair ? "gather2d_pair" : "gather2d"));
+    return DPR_OK;
+}
+
+// Float32, images of at least 64 x 64 pixels with 16-byte rows, spatially sorted points: the box of every (CTA, pose) is
+// staged in shared memory with cp.async (dpr_pullback_box.cuh).  Returns DPR_ERR_UNSUPPORTED without touching anything when
+// the sorted copy of the points is not available (the caller then takes pullback_gather2d).
+// Selected automatically for 3-d points (config 2's shape) when box_auto() says so; pullback_algo 6 forces it.  The
+// environment variable DPR_BOX_AUTO (0 / 1, read once) overrides the built-in default for A/B measurements.
+constexpr bool kBoxAutoDefault = false;
+static bool box_auto() {
+    static const bool on = [] {
+        const char* e = getenv("DPR_BOX_AUTO");
+        return e ? (e[0] == '1') : kBoxAutoDefault;
+    }();
+    return on;
+}
+template <int N_IN>
+static int pullback_box2d(const PullbackArgs<float>& a, const DeviceInfo& dev) {
+    constexpr int K = 4;
+    if (!use_sort(a)) return DPR_ERR_UNSUPPORTED;
+    Grid<float, 2> grid;
+    grid.cells = 1;
+    for (int k = 0; k < 2; ++k) {
+        grid.g[k] = (int)a.grid[k];
+        grid.scale[k] = float(a.grid[k]) / 2.f;  // src/raster_pullback.jl:29
+        grid.cells *= a.grid[k];
+    }
+    int rc = zero_gradients(a);
+    if (rc != DPR_OK) return rc;
+    const SortPlan sp = make_sort_plan(N_IN, a.P, 4, a.point_weight != nullptr, 256);
+    rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
+    if (rc != DPR_OK) return rc;
+    char* ws = static_cast<char*>(a.workspace);
+    const float* pts = reinterpret_cast<const float*>(ws + sp.off_points);
+    const float* pwt = a.point_weight ? reinterpret_cast<const float*>(ws + sp.off_pw) : nullptr;
+    const int32_t* perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
+    const int threads = 256;
+    const int64_t point_chunks = (a.P + (int64_t)threads * K - 1) / ((int64_t)threads * K);
+    int64_t pose_chunk = tuning().pose_chunk;
+    if (pose_chunk <= 0) {       // same chunking as pullback_gather2d
+        const int64_t want_ctas = (int64_t)dev.sm_count * 8 * 4;
+        int64_t pose_chunks = (want_ctas + point_chunks - 1) / point_chunks;
+        if (pose_chunks < 1) pose_chunks = 1;
+        if (pose_chunks > a.B) pose_chunks = a.B;
+        pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
+        if (pose_chunk < 8) pose_chunk = a.B < 8 ? a.B : 8;
+    }
+    if (pose_chunk > 512) pose_chunk = 512;
+    if (pose_chunk > a.B) pose_chunk = a.B;
+    const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
+    // d_background CTAs inside the launch, as in pullback_gather2d
+    int bg_ctas = 0;
+    const int64_t img_bytes = grid.cells * (int64_t)sizeof(float);
+    if (a.d_background && img_bytes <= ((int64_t)512 << 10) && point_chunks >= 8 && pose_chunk >= 8) {
+        int64_t n = (pose_chunk * img_bytes + ((int64_t)3 << 20) - 1) / ((int64_t)3 << 20);
+        if (n < 1) n = 1;
+        if (n > pose_chunk) n = pose_chunk;
+        if (n * 4 <= point_chunks) bg_ctas = (int)n;
+    }
+    if (!bg_ctas) {
+        rc = launch_background_sum(a, grid.cells, dev);
+        if (rc != DPR_OK) return rc;
+    }
+    if ((point_chunks + bg_ctas) * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
+    const size_t smem = box_pullback_smem((int)pose_chunk, N_IN);
+    const int head_bytes = (int)(smem - sizeof(float) * 2 * kBoxStageFloats);
+    auto launch = [&](auto kern) -> int {
+        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchScope scope("pullback_box2d", a.stream);
+        kern<<<(unsigned)((point_chunks + bg_ctas) * pose_chunks), threads, smem, a.stream>>>(
+            a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
+            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk,
+            a.d_background, bg_ctas, head_bytes);
+        return DPR_OK;
+    };
+    rc = a.point_weight ? launch(pullback_box2d_kernel<N_IN, K, true>) : launch(pullback_box2d_kernel<N_IN, K, false>);
+    if (rc != DPR_OK) return rc;
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_PULLBACK, "box2d_sorted");
     return DPR_OK;
 }
 
@@ -603,6 +684,16 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
             if (worth && a.P > 0 && a.B > 0) {
                 return a.n_in == 2 ? pullback_win2d<2>(a, dev) : pullback_win2d<3>(a, dev);
             }
+        }
+        // box-staged kernel: images of at least 64 x 64 pixels with 16-byte rows, sorted points.  Automatic for 3-d points
+        // with enough poses to pipeline (config 2's shape); 2-d clouds (config 4: 1 M points, blobs of ~15 pixels in a
+        // 512 x 512 image) would copy 16 KB boxes for 1.6 KB of useful pixels and stay on the L1 kernel.
+        if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && a.grid[0] >= kBoxSize && a.grid[1] >= kBoxSize &&
+            (a.grid[0] % 4) == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && a.P > 0 && a.B > 0 &&
+            a.P < (int64_t)0x3fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff &&
+            (algo == 6 || (algo == 0 && box_auto() && a.n_in == 3 && a.P >= 16384 && a.B >= 16))) {
+            const int rc = a.n_in == 2 ? pullback_box2d<2>(a, dev) : pullback_box2d<3>(a, dev);
+            if (rc != DPR_ERR_UNSUPPORTED) return rc;      // no sorted copy of the points: the L1 kernel below
         }
     }
     if (a.n_out == 2 && tuning().pullback_algo != 1 && a.P < (int64_t)0x3fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff) {

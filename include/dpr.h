@@ -130,7 +130,9 @@ enum dpr_option {
     DPR_OPT_FORWARD_ALGO = 0,   /* 0 auto, 1 global-reduction kernel, 2 shared-memory tile kernel            */
     DPR_OPT_PULLBACK_ALGO = 1,  /* 0 auto, 1 generic gather kernel, 2 2-d kernel (paired loads), 3 2-d kernel (scalar loads),
                                    4 2-d kernel with TMA-staged pose images (Float32, image must fit shared memory),
-                                   5 2-d kernel with TMA-staged windows of larger pose images (Float32, 16-byte rows) */
+                                   5 2-d kernel with TMA-staged windows of larger pose images (Float32, 16-byte rows),
+                                   6 2-d kernel with cp.async-staged 64 x 64 boxes (Float32, images >= 64 x 64, 16-byte rows,
+                                     sorted points) */
     DPR_OPT_TILE_SMEM_BYTES = 2,/* shared-memory budget per CTA for tiles (0 = default)                       */
     DPR_OPT_POINT_SPLIT = 3,    /* forward: force the number of point splits per (pose, slab) (0 = auto)      */
     DPR_OPT_POSE_CHUNK = 4,     /* pullback: force poses per CTA (0 = auto)                                   */

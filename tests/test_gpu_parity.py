@@ -383,6 +383,34 @@ def test_pullback_tma_staged_windows(n_in, weights, grid, B, pose_chunk):
         assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, k
 
 
+@pytest.mark.parametrize("n_in", [2, 3])
+@pytest.mark.parametrize("weights", [True, False])
+@pytest.mark.parametrize("grid,B,pose_chunk,P,spread", [((64, 64), 9, 0, 5003, 1.0), ((128, 96), 150, 70, 20011, 1.0),
+                                                       ((256, 256), 40, 0, 30000, 1.0), ((68, 200), 33, 5, 3001, 2.5),
+                                                       ((128, 96), 20, 0, 200000, 1.0), ((96, 128), 17, 1, 60000, 0.3)])
+def test_pullback_box_staged(n_in, weights, grid, B, pose_chunk, P, spread):
+    """cp.async-staged 64 x 64 boxes (dpr_pullback_box.cuh): sparse clouds send most warps to the global-load path, dense
+    ones (200 k points, or a cloud shrunk to 0.3) to the shared-memory path; a cloud blown up by 2.5 leaves the image, and
+    boxes get clamped at every image border.  Same values either way: must match the L1 kernel to rounding."""
+    d = make_inputs(600 + n_in, n_in, 2, P, B, grid, np.float32, weights)
+    d["points"] = np.asfortranarray(d["points"] * np.float32(spread))
+    _, pb_ref = _oracle_pair(d, grid, np.float32)
+    ds, args = to_dev(d["ds_dout"], torch.float32), dev_args(d, np.float32)
+    with forced(pullback_algo=6, point_sort=1, pose_chunk=pose_chunk):
+        pb = dpr_b200.raster_pullback_(ds, *args)
+        assert dpr_b200.last_path(1) == "box2d_sorted"
+    with forced(pullback_algo=3, point_sort=1, pose_chunk=pose_chunk):
+        pb3 = dpr_b200.raster_pullback_(ds, *args)
+        assert dpr_b200.last_path(1) == "gather2d_sorted"
+    for k in FIELDS:
+        assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[np.float32], (grid, k)
+        assert rel_l2(to_np(getattr(pb, k)), to_np(getattr(pb3, k))) <= 2e-6, (grid, k)
+    with forced(pullback_algo=6, point_sort=2):            # no sorted copy: falls back to the L1 kernel, never fails
+        pb2 = dpr_b200.raster_pullback_(ds, *args)
+        assert dpr_b200.last_path(1).startswith("gather2d")
+    assert rel_l2(to_np(pb2.points), pb_ref.points) <= TOL[np.float32]
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n_in", [2, 3])
 @pytest.mark.parametrize("weights", [True, False])
