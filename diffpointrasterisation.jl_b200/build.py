@@ -10,8 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdpr.so")
 SOURCES = ["dpr_api.cu", "dpr_forward.cu", "dpr_pullback.cu", "dpr_comm.cu"]
-HEADERS = ["dpr_common.cuh", "dpr_forward_fast.cuh", "dpr_forward_radial.cuh", "dpr_pullback_fast.cuh", "dpr_pullback_box.cuh", "dpr_pullback_tma.cuh",
-           "dpr_pullback_win.cuh", "dpr_sort.cuh", "dpr_internal.h", os.path.join("..", "..", "include", "dpr.h")]
+HEADERS = ["dpr_common.cuh", "dpr_forward_fast.cuh", "dpr_forward_radial.cuh", "dpr_pullback_fast.cuh", "dpr_pullback_tma.cuh",
+           "dpr_sort.cuh", "dpr_tile3d.cuh", "dpr_internal.h", os.path.join("..", "..", "include", "dpr.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-fmad=true",
     "-Xcompiler", "-fPIC,-O2,-Wall", "-shared", "-cudart", "shared", "-ldl", "--threads", "4",

@@ -3,7 +3,9 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <mutex>
+#include <utility>
 #include <vector>
 
 #include "dpr_internal.h"
@@ -52,6 +54,19 @@ int cuda_fail(cudaError_t e, const char* what) {
     snprintf(tl_error, sizeof(tl_error), "%s: %s (%s)", what, cudaGetErrorName(e), cudaGetErrorString(e));
     cudaGetLastError();  // clear the sticky-free error state
     return DPR_ERR_CUDA;
+}
+
+// largest dynamic shared-memory size granted so far per (kernel, device)
+static std::mutex g_smem_mutex;
+static std::map<std::pair<const void*, int>, size_t> g_smem_granted;
+int opt_in_smem(const void* kernel, size_t bytes, int device) {
+    if (bytes <= 48 * 1024) return DPR_OK;          // available without opting in
+    std::lock_guard<std::mutex> lock(g_smem_mutex);
+    size_t& have = g_smem_granted[std::make_pair(kernel, device)];
+    if (bytes <= have) return DPR_OK;
+    DPR_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    have = bytes;
+    return DPR_OK;
 }
 
 // per-device attribute cache (the only global mutable state besides options and the host staging arenas)
@@ -164,18 +179,35 @@ struct HostArena {
     void* ws[NSTREAM] = {nullptr, nullptr, nullptr};   // per-stream kernel workspace (dpr_workspace_bytes)
     size_t ws_bytes = 0;
 };
-static std::mutex g_arena_mutex;
+static std::mutex g_arena_mutex[64];     // one lock per device: a process driving several GPUs from several threads is not serialised
 static HostArena g_arena[64];
 
-static int arena_get(HostArena*& out) {
-    int dev = -1;
+static int arena_device(int& dev) {
+    dev = -1;
     DPR_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
+    return DPR_OK;
+}
+// caller holds g_arena_mutex[dev]
+static int arena_get(int dev, HostArena*& out) {
     HostArena& a = g_arena[dev];
     if (a.device != dev) {
-        for (int i = 0; i < NSTREAM; ++i) DPR_CUDA_TRY(cudaStreamCreateWithFlags(&a.streams[i], cudaStreamNonBlocking));
-        DPR_CUDA_TRY(cudaEventCreateWithFlags(&a.shared_ready, cudaEventDisableTiming));
-        for (int i = 0; i < NSTREAM; ++i) DPR_CUDA_TRY(cudaMalloc(&a.ws[i], 4096));
+        // create everything or nothing: a failed call must not leave half an arena behind (the next call would create
+        // the streams again and leak the first set)
+        cudaError_t e = cudaSuccess;
+        for (int i = 0; i < NSTREAM && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&a.streams[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a.shared_ready, cudaEventDisableTiming);
+        for (int i = 0; i < NSTREAM && e == cudaSuccess; ++i) e = cudaMalloc(&a.ws[i], 4096);
+        if (e != cudaSuccess) {
+            for (int i = 0; i < NSTREAM; ++i) {
+                if (a.streams[i]) cudaStreamDestroy(a.streams[i]);
+                if (a.ws[i]) cudaFree(a.ws[i]);
+                a.streams[i] = nullptr; a.ws[i] = nullptr;
+            }
+            if (a.shared_ready) cudaEventDestroy(a.shared_ready);
+            a.shared_ready = nullptr;
+            return cuda_fail(e, "host arena setup");
+        }
         a.ws_bytes = 4096;
         a.device = dev;
     }
@@ -210,9 +242,12 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
     if (rc != DPR_OK) return rc;
     if ((P > 0 && !points) || (B > 0 && (!rotation || !translation || !out))) return DPR_ERR_NULL_POINTER;
     if (B == 0) return DPR_OK;
-    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    int dev_id = -1;
+    rc = arena_device(dev_id);
+    if (rc != DPR_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mutex[dev_id]);
     HostArena* ar = nullptr;
-    rc = arena_get(ar);
+    rc = arena_get(dev_id, ar);
     if (rc != DPR_OK) return rc;
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) cells *= grid[k];
@@ -289,9 +324,12 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
     if (rc != DPR_OK) return rc;
     if ((P > 0 && (!points || !h_dp)) || (B > 0 && (!rotation || !translation || !ds_dout || !h_drot || !h_dtr)))
         return DPR_ERR_NULL_POINTER;
-    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    int dev_id = -1;
+    rc = arena_device(dev_id);
+    if (rc != DPR_OK) return rc;
+    std::lock_guard<std::mutex> lock(g_arena_mutex[dev_id]);
     HostArena* ar = nullptr;
-    rc = arena_get(ar);
+    rc = arena_get(dev_id, ar);
     if (rc != DPR_OK) return rc;
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) cells *= grid[k];
@@ -496,7 +534,7 @@ int dpr_host_release(void) {
     int dev = -1;
     DPR_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
-    std::lock_guard<std::mutex> lock(g_arena_mutex);
+    std::lock_guard<std::mutex> lock(g_arena_mutex[dev]);
     HostArena& a = g_arena[dev];
     if (a.device != dev) return DPR_OK;
     for (int i = 0; i < NSTREAM; ++i) { if (a.slot[i]) cudaFree(a.slot[i]); a.slot[i] = nullptr; }
@@ -513,13 +551,14 @@ int dpr_host_release(void) {
 int dpr_set_option(int option, int64_t value) {
     if (value < 0) return DPR_ERR_BAD_OPTION;
     switch (option) {
-        case DPR_OPT_FORWARD_ALGO: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.forward_algo = value; return DPR_OK;
-        case DPR_OPT_PULLBACK_ALGO: if (value > 6) return DPR_ERR_BAD_OPTION; g_tuning.pullback_algo = value; return DPR_OK;
+        case DPR_OPT_FORWARD_ALGO: if (value > 3) return DPR_ERR_BAD_OPTION; g_tuning.forward_algo = value; return DPR_OK;
+        case DPR_OPT_PULLBACK_ALGO: if (value > 7 || value == 5 || value == 6) return DPR_ERR_BAD_OPTION; g_tuning.pullback_algo = value; return DPR_OK;
         case DPR_OPT_TILE_SMEM_BYTES: g_tuning.tile_smem_bytes = value; return DPR_OK;
         case DPR_OPT_POINT_SPLIT: g_tuning.point_split = value; return DPR_OK;
         case DPR_OPT_POSE_CHUNK: g_tuning.pose_chunk = value; return DPR_OK;
         case DPR_OPT_FORWARD_ACCUM: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.forward_accum = value; return DPR_OK;
         case DPR_OPT_POINT_SORT: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.point_sort = value; return DPR_OK;
+        case DPR_OPT_TILE3D_TMA: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.tile3d_tma = value; return DPR_OK;
         default: return DPR_ERR_BAD_OPTION;
     }
 }
@@ -532,6 +571,7 @@ int64_t dpr_get_option(int option) {
         case DPR_OPT_POSE_CHUNK: return g_tuning.pose_chunk;
         case DPR_OPT_FORWARD_ACCUM: return g_tuning.forward_accum;
         case DPR_OPT_POINT_SORT: return g_tuning.point_sort;
+        case DPR_OPT_TILE3D_TMA: return g_tuning.tile3d_tma;
         default: return -1;
     }
 }

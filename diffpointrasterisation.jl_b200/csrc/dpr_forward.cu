@@ -14,6 +14,7 @@
 #include "dpr_common.cuh"
 #include "dpr_internal.h"
 #include "dpr_sort.cuh"
+#include "dpr_tile3d.cuh"
 
 namespace dpr {
 
@@ -416,7 +417,8 @@ static int forward_global(const ForwardArgs<T>& a, const DeviceInfo& dev) {
 template <typename T>
 static bool plan_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, TileParams<T>& tp, size_t& smem_bytes, bool& use_fast) {
     const int64_t g0 = a.grid[0], g1 = a.grid[1];
-    int64_t budget = tuning().tile_smem_bytes > 0 ? tuning().tile_smem_bytes : (int64_t)dev.max_smem_optin - 1024;
+    const int64_t opt_budget = tuning().tile_smem_bytes;
+    int64_t budget = opt_budget > 0 ? opt_budget : (int64_t)dev.max_smem_optin - 1024;
     if (budget > (int64_t)dev.max_smem_optin - 1024) budget = (int64_t)dev.max_smem_optin - 1024;
     // Float32 takes the fixed-point kernel (dpr_forward_fast.cuh), which needs room for its per-warp queues and, with
     // point weights, 256 bytes of workspace for their statistics
@@ -484,7 +486,7 @@ static int forward_tile2d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
     }
     const TileParams<T>& tpl = tp;
     auto kern = fwd_splat_tile2d_kernel<T, N_IN>;
-    DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+    { const int rcs = opt_in_smem_once(kern, smem_bytes, dev); if (rcs != DPR_OK) return rcs; }
     const int64_t ctas = a.B * tp.slabs * tp.splits;
     {
         LaunchScope scope("fwd_splat_tile2d", a.stream);
@@ -544,7 +546,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
             fp.per_split = (int)(chunks_per_split * kChunk);
             const int64_t ctas = a.B * tp.splits;
             auto launch = [&](auto kern) -> int {
-                DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+                { const int rcs = opt_in_smem_once(kern, smem_bytes, dev); if (rcs != DPR_OK) return rcs; }
                 LaunchScope scope("fwd_tile2d_radial", a.stream);
                 kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(pts4, rmax, a.rotation, a.translation, a.background,
                                                                      a.out_weight, a.out, grid, rp.n_chunks, fp);
@@ -583,7 +585,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
         // per row make the bank (x + 4 y) mod 32.
         if ((a.grid[0] % 32) == 0) {
             const size_t padded = ((size_t)tp.rows * (size_t)(a.grid[0] + 4) * 4 + 127) / 128 * 128 + fast_extra_smem(true) + 128;
-            if (padded <= (size_t)dev.max_smem_optin) {
+            if (padded + 1024 <= (size_t)dev.max_smem_optin) {      // same reserve as plan_tile2d: static smem of the kernel
                 fp.pitch = (int)a.grid[0] + 4;
                 smem_bytes = padded;
             }
@@ -591,7 +593,7 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     }
     const int64_t ctas = a.B * tp.slabs * tp.splits;
     auto launch = [&](auto kern) -> int {
-        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        { const int rcs = opt_in_smem_once(kern, smem_bytes, dev); if (rcs != DPR_OK) return rcs; }
         LaunchScope scope("fwd_tile2d_fast", a.stream);
         kern<<<(unsigned)ctas, 1024, smem_bytes, a.stream>>>(pts, a.rotation, a.translation, a.background,
                                                              a.out_weight, pwt, a.out, grid, (int)a.P, fp);
@@ -608,9 +610,51 @@ static int forward_tile2d_fast(const ForwardArgs<float>& a, const DeviceInfo& de
     return DPR_OK;
 }
 
+// 3-d grids: per-pose tile binning + one CTA per (pose, tile) accumulating in shared memory (dpr_tile3d.cuh)
+template <typename T, int N_IN>
+static int forward_tile3d(const ForwardArgs<T>& a, const DeviceInfo& dev, const t3::Plan& pl) {
+    const Grid<T, 3> grid = t3::make_grid3<T>(a.grid);
+    char* ws = static_cast<char*>(a.workspace);
+    int rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, false, dev, a.stream);
+    if (rc != DPR_OK) return rc;
+    const size_t smem = sizeof(T) * (size_t)t3::kTileCells;
+    auto kern = t3::fwd_tile3d_kernel<T, N_IN>;
+    rc = opt_in_smem_once(kern, smem, dev);
+    if (rc != DPR_OK) return rc;
+    const t3::Pt4<T>* pts4 = reinterpret_cast<const t3::Pt4<T>*>(ws + pl.off_pts4);
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ws + pl.tile_scan.off_data);
+    const uint32_t* entries = reinterpret_cast<const uint32_t*>(ws + pl.off_entries);
+    const uint32_t* pw_stats = a.point_weight ? reinterpret_cast<const uint32_t*>(ws + pl.sort_scan.off_ticket) : nullptr;
+    // fixed-point fractional bits (Float32): headroom for ~64x the mean number of contributions per cell before a 32-bit
+    // cell wraps (a wrap is detected exactly and the tile redone with float atomics); 0 = float atomics only
+    int fixed_bits = 0;
+    if (sizeof(T) == 4 && tuning().forward_accum != 1) {
+        const double per_cell = 8.0 * (double)a.P / (double)grid.cells;
+        int head = 6;
+        while (head < 14 && (double)(1 << head) < 64.0 * per_cell + 64.0) ++head;
+        fixed_bits = 32 - head > 22 ? 22 : 32 - head;
+    }
+    for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
+        const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
+        rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
+        if (rc != DPR_OK) return rc;
+        LaunchScope scope("fwd_tile3d", a.stream);
+        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, smem, a.stream>>>(pts4, entries, cnt, a.rotation, a.translation,
+                                                                              a.background, a.out_weight, a.out, grid, pl.tg, b0,
+                                                                              pw_stats, a.P, fixed_bits);
+    }
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_FORWARD, fixed_bits ? "tile3d_binned_fixed" : "tile3d_binned");
+    return DPR_OK;
+}
+
 template <typename T>
 int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
     const int64_t algo = tuning().forward_algo;
+    if (a.n_out == 3 && a.n_in == 3 && algo != 1 && a.P > 0 && a.B > 0 && (algo == 3 || t3::worthwhile(a.grid, a.P, a.B))) {
+        const t3::Plan pl = t3::make_plan(a.n_in, a.grid, a.P, a.B, (int)sizeof(T), false);
+        if (pl.ok && a.workspace && a.workspace_bytes >= pl.total) return forward_tile3d<T, 3>(a, dev, pl);
+    }
     if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && algo != 1 && a.P > 0 && a.B > 0) {
         TileParams<T> tp;
         size_t smem = 0;
@@ -636,12 +680,17 @@ int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
 template int forward_dispatch<float>(const ForwardArgs<float>&, const DeviceInfo&);
 template int forward_dispatch<double>(const ForwardArgs<double>&, const DeviceInfo&);
 
-size_t forward_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t, int sizeof_T) {
+size_t forward_workspace_bytes(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, int sizeof_T) {
     // point-weight statistics (256 B) + room for the spatially sorted copy of the points and their run boxes
     const SortPlan sp = make_sort_plan(n_in, P, sizeof_T, true, 256);
     const size_t morton = sp.total + sizeof(float) * 2 * (size_t)n_in * (size_t)((P + 1023) / 1024) + 256;
     const size_t radial = P >= 8192 ? make_radial_plan(P, 256).total + 256 : 0;   // radial kernel: large clouds only
-    return morton > radial ? morton : radial;
+    size_t need = morton > radial ? morton : radial;
+    if (n_out == 3 && n_in == 3 && grid) {     // tile-binned 3-d path: sorted copy, keys, counters, P x poses entries
+        const t3::Plan pl = t3::make_plan(n_in, grid, P, B, sizeof_T, false);
+        if (pl.ok && (tuning().forward_algo == 3 || t3::worthwhile(grid, P, B)) && pl.total > need) need = pl.total;
+    }
+    return need;
 }
 
 }  // namespace dpr

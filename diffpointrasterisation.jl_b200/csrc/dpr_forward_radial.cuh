@@ -344,7 +344,9 @@ fwd_tile2d_radial_kernel(const float4* __restrict__ pts4, const float* __restric
 
         // two points in flight per thread (the points stream from L2: one chunk ahead left ~27 % of the stall cycles on
         // the load's scoreboard); the copy is padded, so the prefetch never needs a bounds test
-        const float4* __restrict__ next = pts4 + (size_t)c_begin * kChunk + threadIdx.x;
+        // (a split that starts beyond the last chunk - (Q-1)*ceil(n/Q) can exceed n - has no work: its prefetch is clamped
+        // into the padding, which covers chunks n .. n+2)
+        const float4* __restrict__ next = pts4 + (size_t)(c_begin < n_chunks_total ? c_begin : n_chunks_total) * kChunk + threadIdx.x;
         float4 q0 = ldg_stream4(next), q1 = ldg_stream4(next + kChunk);
         next += 2 * kChunk;
         auto pop = [&]() -> float4 {

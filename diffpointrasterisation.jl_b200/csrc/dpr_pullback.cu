@@ -12,11 +12,12 @@
 // CTA as one REDG per (pose, value).  CTAs are ordered so that neighbours work on the same poses at the same time,
 // which keeps the ds_dout images they gather from resident in L1/L2.
 #include <cmath>
-#include <cstdlib>
+#include <cstring>
 
 #include "dpr_common.cuh"
 #include "dpr_internal.h"
 #include "dpr_sort.cuh"
+#include "dpr_tile3d.cuh"
 
 namespace dpr {
 
@@ -296,9 +297,7 @@ static int pullback_global(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 
 }  // namespace dpr
 #include "dpr_pullback_fast.cuh"
-#include "dpr_pullback_box.cuh"
 #include "dpr_pullback_tma.cuh"
-#include "dpr_pullback_win.cuh"
 namespace dpr {
 
 // zero everything that is accumulated with REDG (the five fill! calls of ext/DiffPointRasterisationCUDAExt.jl:272-276)
@@ -337,6 +336,115 @@ static int zero_gradients(const PullbackArgs<T>& a) {
         zero_buffers_kernel<<<(unsigned)blocks, 256, 0, a.stream>>>(z);
     }
     DPR_CUDA_TRY(cudaGetLastError());
+    return DPR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 3-d grids: per-pose tile binning + one CTA per (pose, tile) gathering from its staged ds_dout tile (dpr_tile3d.cuh)
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static const EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        cudaGetLastError();
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+template <typename T, int N_IN>
+static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, const t3::Plan& pl) {
+    constexpr int NR = 3 * N_IN;
+    const Grid<T, 3> grid = t3::make_grid3<T>(a.grid);
+    char* ws = static_cast<char*>(a.workspace);
+    {   // per-pose outputs are accumulated with REDG; d_points / d_point_weight are overwritten by the un-permute pass
+        ZeroList z;
+        z.ptr[0] = a.d_rotation;    z.bytes[0] = sizeof(T) * (unsigned long long)(a.B * NR);
+        z.ptr[1] = a.d_translation; z.bytes[1] = sizeof(T) * (unsigned long long)(a.B * 3);
+        z.ptr[2] = a.d_out_weight;  z.bytes[2] = a.d_out_weight ? sizeof(T) * (unsigned long long)a.B : 0;
+        z.ptr[3] = a.d_background;  z.bytes[3] = a.d_background ? sizeof(T) * (unsigned long long)a.B : 0;
+        z.ptr[4] = nullptr;         z.bytes[4] = 0;
+        LaunchScope scope("zero_gradients", a.stream);
+        zero_buffers_kernel<<<8, 256, 0, a.stream>>>(z);
+    }
+    int rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, true, dev, a.stream);
+    if (rc != DPR_OK) return rc;
+    // tensor-map TMA for the tile loads when the volume qualifies (16-byte rows and base) and the option asks for it
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    bool use_tma = false;
+    if (tuning().tile3d_tma == 1 && (a.grid[0] * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && tensor_map_encoder()) {
+        const cuuint64_t dims[4] = {(cuuint64_t)a.grid[0], (cuuint64_t)a.grid[1], (cuuint64_t)a.grid[2], (cuuint64_t)a.B};
+        const cuuint64_t strides[3] = {(cuuint64_t)a.grid[0] * sizeof(T), (cuuint64_t)a.grid[0] * a.grid[1] * sizeof(T),
+                                       (cuuint64_t)grid.cells * sizeof(T)};
+        const cuuint32_t box[4] = {(cuuint32_t)t3::TX, (cuuint32_t)t3::TY, (cuuint32_t)t3::TZ, 1u};
+        const cuuint32_t es[4] = {1u, 1u, 1u, 1u};
+        const CUresult r = tensor_map_encoder()(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4,
+                                                const_cast<T*>(a.ds_dout), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        use_tma = r == CUDA_SUCCESS;
+    }
+    const size_t smem = sizeof(T) * (size_t)t3::kTileCells;
+    const t3::Pt4<T>* pts4 = reinterpret_cast<const t3::Pt4<T>*>(ws + pl.off_pts4);
+    t3::Pt4<T>* acc4 = reinterpret_cast<t3::Pt4<T>*>(ws + pl.off_acc4);
+    const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ws + pl.tile_scan.off_data);
+    const uint32_t* entries = reinterpret_cast<const uint32_t*>(ws + pl.off_entries);
+    // persistent kernel with cp.async-staged tiles: needs 16-byte rows and a 16-byte aligned volume
+    const bool persistent = !use_tma && (a.grid[0] * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0;
+    auto launch_simple = [&](auto kern, int64_t b0, int64_t nb) -> int {
+        const int rcs = opt_in_smem_once(kern, smem, dev);
+        if (rcs != DPR_OK) return rcs;
+        LaunchScope scope("pullback_tile3d", a.stream);
+        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, smem, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation, a.translation,
+                                                                              a.out_weight, acc4, a.d_rotation, a.d_translation,
+                                                                              a.d_background, a.d_out_weight, grid, pl.tg, b0);
+        return DPR_OK;
+    };
+    auto launch_persistent = [&](int64_t b0, int64_t nb) -> int {
+        auto kern = t3::pullback_tile3d_kernel<T, N_IN>;
+        const size_t smem2 = 2 * smem;
+        const int rcs = opt_in_smem_once(kern, smem2, dev);
+        if (rcs != DPR_OK) return rcs;
+        static int per_sm_cache[2] = {0, 0};                 // resident CTAs per SM (Float32, Float64): a property of the kernel
+        int& per_sm = per_sm_cache[sizeof(T) == 8];
+        if (per_sm == 0) {
+            int n = 0;
+            DPR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, t3::kThreads, smem2));
+            per_sm = n > 0 ? n : 1;
+        }
+        const int64_t n_work = nb * pl.tg.n_tiles;
+        int64_t ctas = (int64_t)dev.sm_count * per_sm;
+        if (ctas > n_work) ctas = n_work;
+        uint32_t* counter = reinterpret_cast<uint32_t*>(ws + pl.tile_scan.off_ticket) + t3::kWorkCounter;
+        LaunchScope scope("pullback_tile3d", a.stream);
+        kern<<<(unsigned)ctas, t3::kThreads, smem2, a.stream>>>(a.ds_dout, pts4, entries, cnt, a.rotation, a.translation, a.out_weight, acc4,
+                                                               a.d_rotation, a.d_translation, a.d_background, a.d_out_weight, grid, pl.tg,
+                                                               b0, (int)n_work, counter);
+        return DPR_OK;
+    };
+    for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
+        const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
+        rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
+        if (rc != DPR_OK) return rc;
+        if (persistent) rc = launch_persistent(b0, nb);
+        else rc = use_tma ? launch_simple(t3::pullback_tile3d_simple_kernel<T, N_IN, true>, b0, nb)
+                          : launch_simple(t3::pullback_tile3d_simple_kernel<T, N_IN, false>, b0, nb);
+        if (rc != DPR_OK) return rc;
+    }
+    {
+        int64_t blocks = (a.P + 255) / 256;
+        if (blocks > (int64_t)dev.sm_count * 16) blocks = (int64_t)dev.sm_count * 16;
+        LaunchScope scope("tile3_unpermute", a.stream);
+        t3::unpermute_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, a.stream>>>(acc4, reinterpret_cast<const int32_t*>(ws + pl.off_perm), a.P,
+                                                                            a.d_points, a.d_point_weight);
+    }
+    DPR_CUDA_TRY(cudaGetLastError());
+    set_last_path(DPR_OP_PULLBACK, use_tma ? "tile3d_binned_tma" : (persistent ? "tile3d_binned_persistent" : "tile3d_binned"));
     return DPR_OK;
 }
 
@@ -426,85 +534,6 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     return DPR_OK;
 }
 
-// Float32, images of at least 64 x 64 pixels with 16-byte rows, spatially sorted points: the box of every (CTA, pose) is
-// staged in shared memory with cp.async (dpr_pullback_box.cuh).  Returns DPR_ERR_UNSUPPORTED without touching anything when
-// the sorted copy of the points is not available (the caller then takes pullback_gather2d).
-// Selected automatically for 3-d points (config 2's shape) when box_auto() says so; pullback_algo 6 forces it.  The
-// environment variable DPR_BOX_AUTO (0 / 1, read once) overrides the built-in default for A/B measurements.
-constexpr bool kBoxAutoDefault = false;
-static bool box_auto() {
-    static const bool on = [] {
-        const char* e = getenv("DPR_BOX_AUTO");
-        return e ? (e[0] == '1') : kBoxAutoDefault;
-    }();
-    return on;
-}
-template <int N_IN>
-static int pullback_box2d(const PullbackArgs<float>& a, const DeviceInfo& dev) {
-    constexpr int K = 4;
-    if (!use_sort(a)) return DPR_ERR_UNSUPPORTED;
-    Grid<float, 2> grid;
-    grid.cells = 1;
-    for (int k = 0; k < 2; ++k) {
-        grid.g[k] = (int)a.grid[k];
-        grid.scale[k] = float(a.grid[k]) / 2.f;  // src/raster_pullback.jl:29
-        grid.cells *= a.grid[k];
-    }
-    int rc = zero_gradients(a);
-    if (rc != DPR_OK) return rc;
-    const SortPlan sp = make_sort_plan(N_IN, a.P, 4, a.point_weight != nullptr, 256);
-    rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
-    if (rc != DPR_OK) return rc;
-    char* ws = static_cast<char*>(a.workspace);
-    const float* pts = reinterpret_cast<const float*>(ws + sp.off_points);
-    const float* pwt = a.point_weight ? reinterpret_cast<const float*>(ws + sp.off_pw) : nullptr;
-    const int32_t* perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
-    const int threads = 256;
-    const int64_t point_chunks = (a.P + (int64_t)threads * K - 1) / ((int64_t)threads * K);
-    int64_t pose_chunk = tuning().pose_chunk;
-    if (pose_chunk <= 0) {       // same chunking as pullback_gather2d
-        const int64_t want_ctas = (int64_t)dev.sm_count * 8 * 4;
-        int64_t pose_chunks = (want_ctas + point_chunks - 1) / point_chunks;
-        if (pose_chunks < 1) pose_chunks = 1;
-        if (pose_chunks > a.B) pose_chunks = a.B;
-        pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
-        if (pose_chunk < 8) pose_chunk = a.B < 8 ? a.B : 8;
-    }
-    if (pose_chunk > 512) pose_chunk = 512;
-    if (pose_chunk > a.B) pose_chunk = a.B;
-    const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
-    // d_background CTAs inside the launch, as in pullback_gather2d
-    int bg_ctas = 0;
-    const int64_t img_bytes = grid.cells * (int64_t)sizeof(float);
-    if (a.d_background && img_bytes <= ((int64_t)512 << 10) && point_chunks >= 8 && pose_chunk >= 8) {
-        int64_t n = (pose_chunk * img_bytes + ((int64_t)3 << 20) - 1) / ((int64_t)3 << 20);
-        if (n < 1) n = 1;
-        if (n > pose_chunk) n = pose_chunk;
-        if (n * 4 <= point_chunks) bg_ctas = (int)n;
-    }
-    if (!bg_ctas) {
-        rc = launch_background_sum(a, grid.cells, dev);
-        if (rc != DPR_OK) return rc;
-    }
-    if ((point_chunks + bg_ctas) * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
-    const size_t smem = box_pullback_smem((int)pose_chunk, N_IN);
-    const int head_bytes = (int)(smem - sizeof(float) * 2 * kBoxStageFloats);
-    auto launch = [&](auto kern) -> int {
-        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchScope scope("pullback_box2d", a.stream);
-        kern<<<(unsigned)((point_chunks + bg_ctas) * pose_chunks), threads, smem, a.stream>>>(
-            a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
-            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk,
-            a.d_background, bg_ctas, head_bytes);
-        return DPR_OK;
-    };
-    rc = a.point_weight ? launch(pullback_box2d_kernel<N_IN, K, true>) : launch(pullback_box2d_kernel<N_IN, K, false>);
-    if (rc != DPR_OK) return rc;
-    DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, "box2d_sorted");
-    return DPR_OK;
-}
-
 // Float32 images that fit a 2- or 3-stage shared-memory ring: TMA-staged kernel (dpr_pullback_tma.cuh)
 template <int N_IN>
 static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, int stages) {
@@ -553,7 +582,7 @@ static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, i
     const size_t smem = tma_pullback_smem(grid.cells, stages, N_IN);
     const bool has_pw = a.point_weight != nullptr;
     auto launch = [&](auto kern) -> int {
-        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        { const int rcs = opt_in_smem_once(kern, smem, dev); if (rcs != DPR_OK) return rcs; }
         LaunchScope scope("pullback_tma2d", a.stream);
         kern<<<(unsigned)(point_chunks * pose_chunks), kTmaConsumers + 32, smem, a.stream>>>(
             a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation, a.d_translation,
@@ -568,92 +597,13 @@ static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, i
     return DPR_OK;
 }
 
-// Float32 images larger than shared memory: TMA-staged windows around the projected centroid of each CTA's points
-// (dpr_pullback_win.cuh).  Needs the spatially sorted copy of the points.
-constexpr int kWinK = 8;
-
-// rows per band for `stages` stages (0: the kernel does not apply)
-static int win_band_rows(const DeviceInfo& dev, int64_t g0, int64_t g1, int stages, int n_in) {
-    const int64_t fixed = (int64_t)win_pullback_smem(g0, 0, stages, n_in) + 1024;
-    int64_t rows = ((int64_t)dev.max_smem_optin - fixed) / stages / (g0 * 4);
-    if (rows > g1) rows = g1;
-    return rows >= 32 ? (int)rows : 0;
-}
-
-static size_t win_centroid_offset(int n_in, int64_t P, bool has_pw) {
-    return (make_sort_plan(n_in, P, 4, has_pw, 256).total + 255) / 256 * 256;
-}
-static size_t win_workspace_bytes(int n_in, int64_t P) {
-    const int64_t ppc = (int64_t)kTmaConsumers * kWinK;
-    return win_centroid_offset(n_in, P, true) + sizeof(float) * (size_t)n_in * (size_t)((P + ppc - 1) / ppc) + 256;
-}
-
-template <int N_IN>
-static int pullback_win2d(const PullbackArgs<float>& a, const DeviceInfo& dev) {
-    constexpr int K = kWinK;
-    Grid<float, 2> grid;
-    grid.cells = 1;
-    for (int k = 0; k < 2; ++k) {
-        grid.g[k] = (int)a.grid[k];
-        grid.scale[k] = float(a.grid[k]) / 2.f;
-        grid.cells *= a.grid[k];
-    }
-    int rc = zero_gradients(a);
-    if (rc != DPR_OK) return rc;
-    rc = launch_background_sum(a, grid.cells, dev);
-    if (rc != DPR_OK) return rc;
-    const bool has_pw = a.point_weight != nullptr;
-    const SortPlan sp = make_sort_plan(N_IN, a.P, 4, has_pw, 256);
-    rc = sort_points<float, N_IN>(a.points, a.point_weight, a.P, a.workspace, sp, dev, a.stream);
-    if (rc != DPR_OK) return rc;
-    char* ws = static_cast<char*>(a.workspace);
-    const float* pts = reinterpret_cast<const float*>(ws + sp.off_points);
-    const float* pwt = has_pw ? reinterpret_cast<const float*>(ws + sp.off_pw) : nullptr;
-    const int32_t* perm = reinterpret_cast<const int32_t*>(ws + sp.off_perm);
-    float* centroid = reinterpret_cast<float*>(ws + win_centroid_offset(N_IN, a.P, has_pw));
-    const int64_t ppc = (int64_t)kTmaConsumers * K;
-    const int64_t point_chunks = (a.P + ppc - 1) / ppc;
-    {
-        LaunchScope scope("chunk_centroid", a.stream);
-        chunk_centroid_kernel<N_IN><<<(unsigned)point_chunks, 256, 0, a.stream>>>(pts, a.P, (int)ppc, centroid);
-    }
-    // pose chunks: fill whole waves of one CTA per SM, keep chunks long enough to amortise the per-point REDGs
-    int64_t pose_chunks = 1;
-    if (tuning().pose_chunk > 0) {
-        pose_chunks = (a.B + tuning().pose_chunk - 1) / tuning().pose_chunk;
-    } else {
-        double best = 1e30;
-        for (int64_t m = 1; m <= 64 && m <= a.B; ++m) {
-            if (a.B / m < 32 && m > 1) break;
-            const int64_t n = point_chunks * m;
-            const int64_t waves = (n + dev.sm_count - 1) / dev.sm_count;
-            const double cost = (double)waves * dev.sm_count / (double)n + 0.01 * m;   // wave inefficiency + REDG overhead
-            if (cost < best) { best = cost; pose_chunks = m; }
-        }
-    }
-    const int64_t pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
-    pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
-    if (point_chunks * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
-    constexpr int stages = 2;   // measured on config 2: 2 stages x 108 rows 2.52 ms, 3 stages x 72 rows 3.38 ms
-    const int wy = win_band_rows(dev, a.grid[0], a.grid[1], stages, N_IN);
-    const size_t smem = win_pullback_smem(a.grid[0], wy, stages, N_IN);
-    auto launch = [&](auto kern) -> int {
-        DPR_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchScope scope("pullback_win2d", a.stream);
-        kern<<<(unsigned)(point_chunks * pose_chunks), kTmaConsumers + 32, smem, a.stream>>>(
-            a.ds_dout, pts, centroid, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation,
-            a.d_translation, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk, wy);
-        return DPR_OK;
-    };
-    rc = has_pw ? launch(pullback_win2d_kernel<N_IN, K, true, 2>) : launch(pullback_win2d_kernel<N_IN, K, false, 2>);
-    if (rc != DPR_OK) return rc;
-    DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, "win2d_sorted");
-    return DPR_OK;
-}
-
 template <typename T>
 int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
+    if (a.n_out == 3 && a.n_in == 3 && tuning().pullback_algo != 1 && a.P > 0 && a.B > 0 &&
+        (tuning().pullback_algo == 7 || (tuning().pullback_algo == 0 && t3::worthwhile(a.grid, a.P, a.B)))) {
+        const t3::Plan pl = t3::make_plan(a.n_in, a.grid, a.P, a.B, (int)sizeof(T), true);
+        if (pl.ok && a.workspace && a.workspace_bytes >= pl.total) return pullback_tile3d<T, 3>(a, dev, pl);
+    }
     if constexpr (sizeof(T) == 4) {
         // TMA-staged kernel: whole pose image on chip, 16-byte aligned images, enough points to fill the CTAs
         const int64_t cells2 = a.n_out == 2 ? a.grid[0] * a.grid[1] : 0;
@@ -668,32 +618,6 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
                 if (a.n_in == 2) return pullback_tma2d<2>(a, dev, stages);
                 if (a.n_in == 3) return pullback_tma2d<3>(a, dev, stages);
             }
-        }
-        // windowed TMA kernel: larger images, rows a multiple of 16 bytes, the sorted copy of the points available
-        if (a.n_out == 2 && (algo == 0 || algo == 5) && (a.n_in == 2 || a.n_in == 3) && (a.grid[0] % 4) == 0 &&
-            a.grid[0] >= 8 && a.grid[1] >= 8 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 &&
-            a.P < (int64_t)0x3fffffff && a.B < (int64_t)0x7fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff &&
-            tuning().point_sort != 2 && a.workspace && a.workspace_bytes >= win_workspace_bytes(a.n_in, a.P) &&
-            win_band_rows(dev, a.grid[0], a.grid[1], 3, a.n_in) > 0) {
-            // Measured on B200 against the L1-gather kernel WITH PAIRED LOADS: config 4 (1 M points, 2-d, 512^2: 32-row
-            // blobs, 54-row bands) 4.23 -> 3.58 ms; config 2 (100 k points, 3-d, 256^2: 86-row blobs, 108-row bands)
-            // 2.12 -> 2.57 ms.
-            // (second half of the session: with scalar corner loads the L1-gather kernel takes config 4 in 3.33 ms, so
-            // the band kernel is no longer selected automatically; it stays available as pullback_algo 5.)
-            const bool worth = algo == 5;
-            if (worth && a.P > 0 && a.B > 0) {
-                return a.n_in == 2 ? pullback_win2d<2>(a, dev) : pullback_win2d<3>(a, dev);
-            }
-        }
-        // box-staged kernel: images of at least 64 x 64 pixels with 16-byte rows, sorted points.  Automatic for 3-d points
-        // with enough poses to pipeline (config 2's shape); 2-d clouds (config 4: 1 M points, blobs of ~15 pixels in a
-        // 512 x 512 image) would copy 16 KB boxes for 1.6 KB of useful pixels and stay on the L1 kernel.
-        if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && a.grid[0] >= kBoxSize && a.grid[1] >= kBoxSize &&
-            (a.grid[0] % 4) == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && a.P > 0 && a.B > 0 &&
-            a.P < (int64_t)0x3fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff &&
-            (algo == 6 || (algo == 0 && box_auto() && a.n_in == 3 && a.P >= 16384 && a.B >= 16))) {
-            const int rc = a.n_in == 2 ? pullback_box2d<2>(a, dev) : pullback_box2d<3>(a, dev);
-            if (rc != DPR_ERR_UNSUPPORTED) return rc;      // no sorted copy of the points: the L1 kernel below
         }
     }
     if (a.n_out == 2 && tuning().pullback_algo != 1 && a.P < (int64_t)0x3fffffff && a.grid[0] * a.grid[1] < (int64_t)0x3fffffff) {
@@ -712,10 +636,14 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 template int pullback_dispatch<float>(const PullbackArgs<float>&, const DeviceInfo&);
 template int pullback_dispatch<double>(const PullbackArgs<double>&, const DeviceInfo&);
 
-size_t pullback_workspace_bytes(int n_in, int, const int64_t*, int64_t P, int64_t, int sizeof_T) {
+size_t pullback_workspace_bytes(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, int sizeof_T) {
     const size_t sorted = make_sort_plan(n_in, P, sizeof_T, true, 256).total;
-    const size_t win = sizeof_T == 4 ? win_workspace_bytes(n_in, P) : 0;
-    return sorted > win ? sorted : win;
+    size_t need = sorted;
+    if (n_out == 3 && n_in == 3 && grid) {     // tile-binned 3-d path
+        const t3::Plan pl = t3::make_plan(n_in, grid, P, B, sizeof_T, true);
+        if (pl.ok && (tuning().pullback_algo == 7 || t3::worthwhile(grid, P, B)) && pl.total > need) need = pl.total;
+    }
+    return need;
 }
 
 }  // namespace dpr

@@ -127,18 +127,20 @@ int dpr_comm_allreduce_sum_f64(dpr_comm_t comm, double* buf, int64_t count, dpr_
 
 /* Introspection / tuning (benchmarks and tests). */
 enum dpr_option {
-    DPR_OPT_FORWARD_ALGO = 0,   /* 0 auto, 1 global-reduction kernel, 2 shared-memory tile kernel            */
+    DPR_OPT_FORWARD_ALGO = 0,   /* 0 auto, 1 global-reduction kernel, 2 shared-memory tile kernel (2-d grids),
+                                   3 tile-binned kernel (3-d grids: CTA per pose x tile, src/raster.jl:27,36-66)  */
     DPR_OPT_PULLBACK_ALGO = 1,  /* 0 auto, 1 generic gather kernel, 2 2-d kernel (paired loads), 3 2-d kernel (scalar loads),
                                    4 2-d kernel with TMA-staged pose images (Float32, image must fit shared memory),
-                                   5 2-d kernel with TMA-staged windows of larger pose images (Float32, 16-byte rows),
-                                   6 2-d kernel with cp.async-staged 64 x 64 boxes (Float32, images >= 64 x 64, 16-byte rows,
-                                     sorted points) */
+                                   (5, 6: round-1 experiments, removed - rejected with DPR_ERR_BAD_OPTION),
+                                   7 tile-binned kernel (3-d grids: CTA per pose x tile with its ds_dout tile on chip) */
     DPR_OPT_TILE_SMEM_BYTES = 2,/* shared-memory budget per CTA for tiles (0 = default)                       */
     DPR_OPT_POINT_SPLIT = 3,    /* forward: force the number of point splits per (pose, slab) (0 = auto)      */
     DPR_OPT_POSE_CHUNK = 4,     /* pullback: force poses per CTA (0 = auto)                                   */
     DPR_OPT_FORWARD_ACCUM = 5,  /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
-    DPR_OPT_POINT_SORT = 6      /* 0 auto, 1 always sort the points first (pullback: spatially; forward: also by
+    DPR_OPT_POINT_SORT = 6,     /* 0 auto, 1 always sort the points first (pullback: spatially; forward: also by
                                    radius for the one-slab Float32 tile kernel), 2 never                      */
+    DPR_OPT_TILE3D_TMA = 7      /* 3-d tile pullback: 0 cooperative 16-byte tile loads, 1 tensor-map TMA
+                                   (cp.async.bulk.tensor.4d; faults on some driver stacks)      */
 };
 int dpr_set_option(int option, int64_t value);
 int64_t dpr_get_option(int option);

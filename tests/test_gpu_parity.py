@@ -358,59 +358,6 @@ def test_pullback_tma_staged_images(n_in, weights, B, pose_chunk):
             assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, (sort, k)
 
 
-@pytest.mark.parametrize("n_in", [2, 3])
-@pytest.mark.parametrize("weights", [True, False])
-@pytest.mark.parametrize("grid,B,pose_chunk", [((192, 160), 9, 0), ((192, 160), 150, 70), ((256, 400), 70, 0), ((64, 48), 20, 0)])
-def test_pullback_tma_staged_windows(n_in, weights, grid, B, pose_chunk):
-    """Float32 pose images larger than shared memory: per (CTA, pose) a band of full-width rows around the projected
-    centroid of the CTA's sorted points is staged by one TMA bulk copy; stencils outside the band (or touching the
-    left / right image border) take the global-load fallback through the same predicated generic loads.  Images taller
-    and shorter than the band, clouds pushed half out of the image, far-away points, matrices that are not rotations,
-    several rounds / pose chunks."""
-    P = 9001
-    d = make_inputs(4321 + B, n_in, 2, P, B, grid, np.float32, weights)
-    d["points"][:, :3] = np.array([[5.0, -7.0, 1e30], [0.99, -1.0, 1.0]] + ([[0.0, 0.0, 0.0]] if n_in == 3 else []), dtype=np.float32)
-    d["points"][:, 3:200] *= 2.5                      # a halo the window cannot cover: fallback loads
-    d["rotation"][:, :, 1] *= 1.6
-    d["rotation"][:, :, 2] = 0.0
-    d["translation"][:, 3] = (0.9, -0.8)
-    d["translation"][:, 4] = (-1.1, 0.2)
-    _, pb_ref = _oracle_pair(d, grid, np.float32)
-    with forced(pullback_algo=5, pose_chunk=pose_chunk):
-        pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], torch.float32), *dev_args(d, np.float32))
-        assert dpr_b200.last_path(1) == "win2d_sorted"
-    for k in FIELDS:
-        assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, k
-
-
-@pytest.mark.parametrize("n_in", [2, 3])
-@pytest.mark.parametrize("weights", [True, False])
-@pytest.mark.parametrize("grid,B,pose_chunk,P,spread", [((64, 64), 9, 0, 5003, 1.0), ((128, 96), 150, 70, 20011, 1.0),
-                                                       ((256, 256), 40, 0, 30000, 1.0), ((68, 200), 33, 5, 3001, 2.5),
-                                                       ((128, 96), 20, 0, 200000, 1.0), ((96, 128), 17, 1, 60000, 0.3)])
-def test_pullback_box_staged(n_in, weights, grid, B, pose_chunk, P, spread):
-    """cp.async-staged 64 x 64 boxes (dpr_pullback_box.cuh): sparse clouds send most warps to the global-load path, dense
-    ones (200 k points, or a cloud shrunk to 0.3) to the shared-memory path; a cloud blown up by 2.5 leaves the image, and
-    boxes get clamped at every image border.  Same values either way: must match the L1 kernel to rounding."""
-    d = make_inputs(600 + n_in, n_in, 2, P, B, grid, np.float32, weights)
-    d["points"] = np.asfortranarray(d["points"] * np.float32(spread))
-    _, pb_ref = _oracle_pair(d, grid, np.float32)
-    ds, args = to_dev(d["ds_dout"], torch.float32), dev_args(d, np.float32)
-    with forced(pullback_algo=6, point_sort=1, pose_chunk=pose_chunk):
-        pb = dpr_b200.raster_pullback_(ds, *args)
-        assert dpr_b200.last_path(1) == "box2d_sorted"
-    with forced(pullback_algo=3, point_sort=1, pose_chunk=pose_chunk):
-        pb3 = dpr_b200.raster_pullback_(ds, *args)
-        assert dpr_b200.last_path(1) == "gather2d_sorted"
-    for k in FIELDS:
-        assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[np.float32], (grid, k)
-        assert rel_l2(to_np(getattr(pb, k)), to_np(getattr(pb3, k))) <= 2e-6, (grid, k)
-    with forced(pullback_algo=6, point_sort=2):            # no sorted copy: falls back to the L1 kernel, never fails
-        pb2 = dpr_b200.raster_pullback_(ds, *args)
-        assert dpr_b200.last_path(1).startswith("gather2d")
-    assert rel_l2(to_np(pb2.points), pb_ref.points) <= TOL[np.float32]
-
-
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("n_in", [2, 3])
 @pytest.mark.parametrize("weights", [True, False])
@@ -689,7 +636,7 @@ def test_randomised_shapes_and_misaligned_buffers():
             assert rel_l2(to_np(out), out_ref) <= TOL[dtype], (trial, "fwd", fa, grid, P, B)
         palgos = (0, 1, 2, 3) if n_out == 2 else (0, 1)
         if n_out == 2 and dtype == np.float32 and (grid[0] * grid[1]) % 4 == 0:
-            palgos += (4, 5)       # 5 (windowed TMA) needs 16-byte rows and aligned images, else the library falls through
+            palgos += (4,)         # TMA-staged whole images: needs 16-byte aligned images, else the library falls through
         for pa in palgos:
             with forced(pullback_algo=pa):
                 pb = dpr_b200.raster_pullback_(ds, *args)
@@ -778,3 +725,55 @@ def test_degenerate_grids(dtype, grid):
             pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], td), *args)
         for k in FIELDS:
             assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (grid, pa, k, dpr_b200.last_path(1))
+
+
+# ---- 3-d grids: tile-binned forward / pullback (dpr_tile3d.cuh) ----------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("grid", [(64, 32, 32), (40, 24, 20), (33, 17, 50), (8, 8, 8), (100, 9, 21)])
+@pytest.mark.parametrize("weights", [True, False])
+def test_tile3d_paths(dtype, grid, weights):
+    """CTA per (pose, tile) with per-pose binned points (src/raster.jl:27,36-66; src/raster_pullback.jl:2-82): grids that
+    are and are not multiples of the 32 x 16 x 16 tile, stencils straddling up to 8 tiles, clipped borders."""
+    d = make_inputs(500 + sum(grid), 3, 3, 30011, 5, grid, dtype, weights)
+    d["points"][:, :7] *= 6.0            # a few points far outside the cube (src/raster.jl:62: skipped per corner)
+    with forced(forward_algo=3, pullback_algo=7):
+        _check(d, grid, dtype, f"tile3d {grid}")
+        assert dpr_b200.last_path(0) == "tile3d_binned" and dpr_b200.last_path(1).startswith("tile3d_binned")
+
+
+def test_tile3d_matches_point_parallel_kernels_and_edge_cases():
+    """Same results as the global-reduction kernels; empty clouds give the background / zero gradients; points exactly on
+    tile faces and cell centres (the discontinuity of d_coord) are binned consistently."""
+    grid = (64, 32, 48)
+    d = make_inputs(91, 3, 3, 50000, 3, grid, np.float64)
+    # identity-like pose and points on a lattice of cell centres / tile faces
+    d["rotation"][:, :, 0] = np.eye(3)
+    d["translation"][:, 0] = 0.0
+    lat = np.stack(np.meshgrid(np.arange(0, 64, 4), np.arange(0, 32, 4), np.arange(0, 48, 4), indexing="ij"), 0).reshape(3, -1)
+    cell = (lat + 0.5) / (np.asarray(grid)[:, None] / 2.0) - 1.0        # coordinates whose coord - 0.5 is an integer
+    d["points"][:, : cell.shape[1]] = cell
+    args = dev_args(d, np.float64)
+    ds = to_dev(d["ds_dout"])
+    with forced(forward_algo=1, pullback_algo=1):
+        out1 = dpr_b200.raster(grid, *args)
+        pb1 = dpr_b200.raster_pullback_(ds, *args)
+    with forced(forward_algo=3, pullback_algo=7):
+        out3 = dpr_b200.raster(grid, *args)
+        pb3 = dpr_b200.raster_pullback_(ds, *args)
+        assert dpr_b200.last_path(0) == "tile3d_binned"
+        e = dpr_b200.empty_f((3, 0), torch.float64, "cuda")
+        assert dpr_b200.raster(grid, e, *args[1:5], None).shape == out3.shape     # P = 0 falls back to the fill
+    assert rel_l2(to_np(out3), to_np(out1)) < 1e-13
+    for k in FIELDS:
+        assert rel_l2(to_np(getattr(pb3, k)), to_np(getattr(pb1, k))) < 1e-11, k
+    out_ref, pb_ref = _oracle_pair(d, grid, np.float64)
+    assert rel_l2(to_np(out3), out_ref) < 1e-10
+    for k in FIELDS:
+        assert rel_l2(to_np(getattr(pb3, k)), getattr(pb_ref, k)) < 1e-10, k
+
+
+def test_tile3d_auto_selected_for_dense_volumes():
+    grid = (64, 64, 64)
+    d = make_inputs(17, 3, 3, 200_000, 16, grid, np.float32, weights=False)
+    _check(d, grid, np.float32, "cfg3 scaled")
+    assert dpr_b200.last_path(0) == "tile3d_binned" and dpr_b200.last_path(1).startswith("tile3d_binned")
