@@ -38,6 +38,16 @@ LaunchScope::LaunchScope(const char* n, cudaStream_t s) : name(n), stream(s), sl
     slot = (int)g_prof.size() - 1;
 }
 LaunchScope::~LaunchScope() {
+    if (g_prof_on.load(std::memory_order_relaxed) == 2) {
+        // checked mode (dpr_profile_enable(2)): wait for the kernel and name it if it faulted
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+            char buf[400];
+            snprintf(buf, sizeof(buf), "kernel %s failed: %s (%s)", name, cudaGetErrorName(e), cudaGetErrorString(e));
+            set_error_message(buf);
+            fprintf(stderr, "libdpr: %s\n", buf);
+        }
+    }
     if (slot < 0) return;
     std::lock_guard<std::mutex> lock(g_prof_mutex);
     if (slot < (int)g_prof.size()) cudaEventRecord(g_prof[slot].e1, stream);
@@ -577,7 +587,7 @@ int64_t dpr_get_option(int option) {
 }
 int dpr_profile_enable(int on) {
     profile_clear();
-    g_prof_on.store(on ? 1 : 0);
+    g_prof_on.store(on == 2 ? 2 : (on ? 1 : 0));
     return DPR_OK;
 }
 int dpr_profile_count(void) {

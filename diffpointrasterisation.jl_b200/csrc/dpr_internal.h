@@ -26,7 +26,7 @@ struct Tuning {
     std::atomic<int64_t> pose_chunk{0};
     std::atomic<int64_t> point_sort{0};      // 0 auto, 1 always sort points spatially, 2 never
     std::atomic<int64_t> forward_accum{0};   // 0 auto (fixed point where eligible), 1 float CAS only
-    std::atomic<int64_t> tile3d_tma{0};      // 3-d tile pullback: 0 cooperative tile loads, 1 tensor-map TMA (cp.async.bulk.tensor)
+    std::atomic<int64_t> tile3d_tma{0};      // 3-d tile pullback: 0 auto (tensor-map TMA), 1 cooperative tile loads only
 };
 
 const Tuning& tuning();

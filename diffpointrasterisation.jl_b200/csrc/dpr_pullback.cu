@@ -373,11 +373,14 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
     }
     int rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, true, dev, a.stream);
     if (rc != DPR_OK) return rc;
-    // tensor-map TMA for the tile loads when the volume qualifies (16-byte rows and base) and the option asks for it
+    // tensor-map TMA for the tile loads when the volume qualifies (16-byte rows and base): one 4-d map over
+    // (g0, g1, g2, B), box = one tile.  Tile origins are multiples of 32 cells, which satisfies the 16-byte box-start rule
+    // (dpr_tile3d.cuh); DPR_OPT_TILE3D_TMA = 1 forces the cooperative loads.
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     bool use_tma = false;
-    if (tuning().tile3d_tma == 1 && (a.grid[0] * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && tensor_map_encoder()) {
+    if (tuning().tile3d_tma != 1 && (a.grid[0] * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 &&
+        a.B < ((int64_t)1 << 31) && tensor_map_encoder()) {
         const cuuint64_t dims[4] = {(cuuint64_t)a.grid[0], (cuuint64_t)a.grid[1], (cuuint64_t)a.grid[2], (cuuint64_t)a.B};
         const cuuint64_t strides[3] = {(cuuint64_t)a.grid[0] * sizeof(T), (cuuint64_t)a.grid[0] * a.grid[1] * sizeof(T),
                                        (cuuint64_t)grid.cells * sizeof(T)};
@@ -389,32 +392,17 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
                                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         use_tma = r == CUDA_SUCCESS;
     }
-    const size_t smem = sizeof(T) * (size_t)t3::kTileCells;
+    const size_t tile_bytes = sizeof(T) * (size_t)t3::kTileCells;
     const t3::Pt4<T>* pts4 = reinterpret_cast<const t3::Pt4<T>*>(ws + pl.off_pts4);
     t3::Pt4<T>* acc4 = reinterpret_cast<t3::Pt4<T>*>(ws + pl.off_acc4);
     const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ws + pl.tile_scan.off_data);
     const uint32_t* entries = reinterpret_cast<const uint32_t*>(ws + pl.off_entries);
-    // persistent kernel with cp.async-staged tiles: needs 16-byte rows and a 16-byte aligned volume
-    const bool persistent = !use_tma && (a.grid[0] * sizeof(T)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0;
-    auto launch_simple = [&](auto kern, int64_t b0, int64_t nb) -> int {
+    auto launch = [&](auto kern, size_t smem, int& per_sm, int64_t b0, int64_t nb) -> int {
         const int rcs = opt_in_smem_once(kern, smem, dev);
         if (rcs != DPR_OK) return rcs;
-        LaunchScope scope("pullback_tile3d", a.stream);
-        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, smem, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation, a.translation,
-                                                                              a.out_weight, acc4, a.d_rotation, a.d_translation,
-                                                                              a.d_background, a.d_out_weight, grid, pl.tg, b0);
-        return DPR_OK;
-    };
-    auto launch_persistent = [&](int64_t b0, int64_t nb) -> int {
-        auto kern = t3::pullback_tile3d_kernel<T, N_IN>;
-        const size_t smem2 = 2 * smem;
-        const int rcs = opt_in_smem_once(kern, smem2, dev);
-        if (rcs != DPR_OK) return rcs;
-        static int per_sm_cache[2] = {0, 0};                 // resident CTAs per SM (Float32, Float64): a property of the kernel
-        int& per_sm = per_sm_cache[sizeof(T) == 8];
-        if (per_sm == 0) {
+        if (per_sm == 0) {                                    // resident CTAs per SM: a property of the kernel
             int n = 0;
-            DPR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, t3::kThreads, smem2));
+            DPR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, t3::kPbThreads, smem));
             per_sm = n > 0 ? n : 1;
         }
         const int64_t n_work = nb * pl.tg.n_tiles;
@@ -422,18 +410,18 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
         if (ctas > n_work) ctas = n_work;
         uint32_t* counter = reinterpret_cast<uint32_t*>(ws + pl.tile_scan.off_ticket) + t3::kWorkCounter;
         LaunchScope scope("pullback_tile3d", a.stream);
-        kern<<<(unsigned)ctas, t3::kThreads, smem2, a.stream>>>(a.ds_dout, pts4, entries, cnt, a.rotation, a.translation, a.out_weight, acc4,
-                                                               a.d_rotation, a.d_translation, a.d_background, a.d_out_weight, grid, pl.tg,
-                                                               b0, (int)n_work, counter);
+        kern<<<(unsigned)ctas, t3::kPbThreads, smem, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation, a.translation, a.out_weight,
+                                                              acc4, a.d_rotation, a.d_translation, a.d_background, a.d_out_weight, grid,
+                                                              pl.tg, b0, (int)n_work, counter);
         return DPR_OK;
     };
+    static int per_sm_cache[2][2] = {{0, 0}, {0, 0}};
     for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
         const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
         rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
         if (rc != DPR_OK) return rc;
-        if (persistent) rc = launch_persistent(b0, nb);
-        else rc = use_tma ? launch_simple(t3::pullback_tile3d_simple_kernel<T, N_IN, true>, b0, nb)
-                          : launch_simple(t3::pullback_tile3d_simple_kernel<T, N_IN, false>, b0, nb);
+        rc = use_tma ? launch(t3::pullback_tile3d_kernel<T, N_IN, true>, t3::kStages * tile_bytes, per_sm_cache[1][sizeof(T) == 8], b0, nb)
+                     : launch(t3::pullback_tile3d_kernel<T, N_IN, false>, tile_bytes, per_sm_cache[0][sizeof(T) == 8], b0, nb);
         if (rc != DPR_OK) return rc;
     }
     {
@@ -444,7 +432,7 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
                                                                             a.d_points, a.d_point_weight);
     }
     DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, use_tma ? "tile3d_binned_tma" : (persistent ? "tile3d_binned_persistent" : "tile3d_binned"));
+    set_last_path(DPR_OP_PULLBACK, use_tma ? "tile3d_binned_tma" : "tile3d_binned_coop");
     return DPR_OK;
 }
 

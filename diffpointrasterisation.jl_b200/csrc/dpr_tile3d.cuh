@@ -240,15 +240,17 @@ __device__ __forceinline__ uint32_t tile_key(const int (&i0)[3], const int (&g)[
     return (((uint32_t)pose_local * (uint32_t)tg.n_tiles + tile) << 3) | pat;
 }
 
-template <typename T, int N_IN, bool SCATTER>
-__global__ void __launch_bounds__(256) tile_bin_kernel(const Pt4<T>* __restrict__ pts4, int P, const T* __restrict__ rotation,
-                                                       const T* __restrict__ translation, Grid<T, 3> grid, TileGeom tg,
-                                                       uint32_t* __restrict__ cnt, uint32_t* __restrict__ entries, int64_t b0) {
+// pass 1: key of every (point, pose) pair - kept for pass 2 - and the histogram
+template <typename T, int N_IN>
+__global__ void __launch_bounds__(256) tile_count_kernel(const Pt4<T>* __restrict__ pts4, int P, const T* __restrict__ rotation,
+                                                         const T* __restrict__ translation, Grid<T, 3> grid, TileGeom tg,
+                                                         uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys, int64_t b0) {
     constexpr int K = 4;
     const int bl = blockIdx.y;
     Pose<T, N_IN, 3> pose;
     load_pose<T, N_IN, 3>(pose, rotation, translation, nullptr, b0 + bl);
     const int lane = threadIdx.x & 31;
+    uint32_t* __restrict__ my_keys = keys + (size_t)bl * (size_t)P;
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int p = (blockIdx.x * K + k) * 256 + (int)threadIdx.x;
@@ -260,317 +262,545 @@ __global__ void __launch_bounds__(256) tile_bin_kernel(const Pt4<T>* __restrict_
             int i0[3];
             T dl[3];
             if (stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) key = tile_key(i0, grid.g, tg, bl);
+            my_keys[p] = key;
         }
         // spatially sorted points: the 32 lanes of a warp share a handful of keys -> one atomic per distinct key
         const unsigned peers = __match_any_sync(0xffffffffu, key);
+        if (key != kNoKey && lane == __ffs(peers) - 1) atomicAdd(cnt + key, (uint32_t)__popc(peers));
+    }
+}
+// pass 2 (after the scan): the sorted point index of every pair goes to its list; no transform, the keys are re-read
+static __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ keys,
+                                                                  uint32_t* __restrict__ entries) {
+    constexpr int K = 4;
+    const uint32_t* __restrict__ my_keys = keys + (size_t)blockIdx.y * (size_t)P;
+    const int lane = threadIdx.x & 31;
+    uint32_t key[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = (blockIdx.x * K + k) * 256 + (int)threadIdx.x;
+        key[k] = p < P ? __ldg(my_keys + p) : kNoKey;
+    }
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        const int p = (blockIdx.x * K + k) * 256 + (int)threadIdx.x;
+        const unsigned peers = __match_any_sync(0xffffffffu, key[k]);
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
-        if (key != kNoKey && lane == leader) {
-            if (SCATTER) base = atomicAdd(cnt + key, (uint32_t)__popc(peers));
-            else atomicAdd(cnt + key, (uint32_t)__popc(peers));
-        }
-        if (SCATTER) {
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (key != kNoKey) entries[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)p;
-        }
+        if (key[k] != kNoKey && lane == leader) base = atomicAdd(cnt + key[k], (uint32_t)__popc(peers));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (key[k] != kNoKey) entries[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)p;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// the 27 sub-lists a tile CTA has to walk: slot i in 0..63, d = i >> 3 (lower-neighbour offset, one bit per
-// dimension), pat = i & 7; the slot is live when pat contains d and the neighbour exists
+// 5. the tile kernels.  Both are PERSISTENT and WARP-SPECIALISED: a CTA has eight consumer warps and one producer warp.
+//
+// The producer warp pulls (pose, tile) work items from a global counter kBatch at a time (one atomic per batch, taken two
+// batches ahead: heavy tiles in the core of the cloud and empty ones at the rim balance out dynamically), and each of its
+// lanes prepares one item: it fetches the bounds of the up to 27 sub-lists the tile has to walk - its own 8 plus, for
+// each of its 7 lower neighbours t - d, those whose pattern contains d - and writes a COMPACT table of the non-empty ones
+// (own interior list first) into a two-batch ring in shared memory, published through an mbarrier.  In the pullback it
+// also issues the tensor-map TMA copies of the ds_dout tiles, kStages - 1 items ahead of the consumers.  The consumers
+// never touch global bookkeeping: they wait on the item's mbarrier, process it, release it.
+//   History (profiles/ncu_r02_*_cfg3_summary.txt): one CTA per item spent 23 % of its stall samples on the first constant
+//   load of a fresh CTA and ~40 % of its instructions on per-CTA set-up; a persistent CTA whose warp 0 did the bookkeeping
+//   one item ahead between two block barriers spent 32 % of its samples in those barriers, waiting for the ticket atomic
+//   and the range loads whenever a tile had little work - and most tiles have.
 // ---------------------------------------------------------------------------------------------------------
-struct Ranges {
-    uint32_t start[64];
-    uint32_t pref[65];
+constexpr int kConsumers = kThreads;              // 8 consumer warps
+constexpr int kCtaThreads = kConsumers + 32;      // + the producer warp
+constexpr int kBatch = 16;                        // items per metadata batch (one per producer lane)
+constexpr int kMaxSlots = 27;
+constexpr int kWorkCounter = 8;                   // word of the tile scan region's header used as the global work counter
+
+struct ItemMeta {
+    int w;                         // work item (>= n_work: no more work)
+    int bl, tx, ty, tz;            // pose (local to the pass), tile coordinates
+    int n_slots;                   // non-empty sub-lists
+    uint32_t total;                // entries over all sub-lists
+    uint32_t n_interior;           // length of the tile's own pattern-0 list (always slot 0 when non-empty)
+    uint32_t base[kMaxSlots];      // sub-list s holds concatenated entries e in [end[s-1], end[s]) at entries[base[s] + e]
+    uint32_t end[kMaxSlots];
 };
-// two phases so that a persistent CTA can issue the loads for its NEXT tile before it processes the current one and
-// consume them afterwards: warp 0, lane handles slots 2*lane and 2*lane+1
-struct RangeLoad { uint32_t s[2], e[2]; };
-__device__ __forceinline__ RangeLoad ranges_issue(const uint32_t* __restrict__ cnt, const TileGeom& tg, int bl, int tx, int ty, int tz) {
-    RangeLoad rl;
-    rl.s[0] = rl.s[1] = rl.e[0] = rl.e[1] = 0u;
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
+
+__device__ __forceinline__ void bar_sync_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
+
+__device__ __forceinline__ void decode_work(ItemMeta& it, int w, const TileGeom& tg) {
+    it.w = w;
+    it.bl = w / tg.n_tiles;
+    const int t = w - it.bl * tg.n_tiles;
+    const int row = tg.nt[0] * tg.nt[1];
+    it.tz = t / row;
+    const int r = t - it.tz * row;
+    it.ty = r / tg.nt[0];
+    it.tx = r - it.ty * tg.nt[0];
+}
+
+// producer lane: the raw bounds of the 27 sub-lists of one item (loads issued here, consumed in meta_finish)
+struct MetaLoad {
+    uint32_t s[kMaxSlots], e[kMaxSlots];
+};
+__device__ __forceinline__ void meta_issue(MetaLoad& ml, const ItemMeta& it, bool valid, const uint32_t* __restrict__ cnt, const TileGeom& tg) {
+    int c = 0;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            const int slot = 2 * lane + h, d = slot >> 3, pat = slot & 7;
-            const int nx = tx - (d & 1), ny = ty - ((d >> 1) & 1), nz = tz - ((d >> 2) & 1);
-            if ((pat & d) == d && nx >= 0 && ny >= 0 && nz >= 0) {
+    for (int d = 0; d < 8; ++d) {
+#pragma unroll
+        for (int pat = 0; pat < 8; ++pat) {
+            if ((pat & d) != d) continue;
+            const int nx = it.tx - (d & 1), ny = it.ty - ((d >> 1) & 1), nz = it.tz - ((d >> 2) & 1);
+            uint32_t s = 0, e = 0;
+            if (valid && nx >= 0 && ny >= 0 && nz >= 0) {
                 const uint32_t tile = (uint32_t)((nz * tg.nt[1] + ny) * tg.nt[0] + nx);
-                const uint32_t key = (((uint32_t)bl * (uint32_t)tg.n_tiles + tile) << 3) | (uint32_t)pat;
-                rl.e[h] = __ldg(cnt + key);                 // after the scatter pass cnt[key] is the END of list `key`
-                rl.s[h] = key ? __ldg(cnt + key - 1) : 0u;
+                const uint32_t key = (((uint32_t)it.bl * (uint32_t)tg.n_tiles + tile) << 3) | (uint32_t)pat;
+                e = __ldg(cnt + key);                       // after the scatter pass cnt[key] is the END of list `key`
+                s = key ? __ldg(cnt + key - 1) : 0u;
             }
+            ml.s[c] = s;
+            ml.e[c] = e;
+            ++c;
         }
     }
-    return rl;
 }
-__device__ __forceinline__ void ranges_finish(Ranges& r, const RangeLoad& rl) {
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        uint32_t len[2];
+__device__ __forceinline__ void meta_finish(ItemMeta& out, const ItemMeta& it, const MetaLoad& ml) {
+    out.w = it.w; out.bl = it.bl; out.tx = it.tx; out.ty = it.ty; out.tz = it.tz;
+    uint32_t run = 0;
+    int n = 0;
+    out.n_interior = ml.e[0] - ml.s[0];                     // combination 0 is (d = 0, pattern = 0)
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            r.start[2 * lane + h] = rl.s[h];
-            len[h] = rl.e[h] - rl.s[h];
+    for (int c = 0; c < kMaxSlots; ++c) {
+        const uint32_t len = ml.e[c] - ml.s[c];
+        if (len) {
+            out.base[n] = ml.s[c] - run;
+            run += len;
+            out.end[n] = run;
+            ++n;
         }
-        const uint32_t mine = len[0] + len[1];
-        uint32_t incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl += t;
-        }
-        r.pref[2 * lane] = incl - mine;
-        r.pref[2 * lane + 1] = incl - mine + len[0];
-        if (lane == 31) r.pref[64] = incl;
     }
-}
-__device__ __forceinline__ void build_ranges(Ranges& r, const uint32_t* __restrict__ cnt, const TileGeom& tg, int bl,
-                                             int tx, int ty, int tz) {
-    const RangeLoad rl = ranges_issue(cnt, tg, bl, tx, ty, tz);
-    ranges_finish(r, rl);
+    out.n_slots = n;
+    out.total = run;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// helpers shared by the tile kernels
-// ---------------------------------------------------------------------------------------------------------
-// words of the 256-byte header of the pre-sort scan region (cleared with it): [0] scan ticket, then the point-weight
-// statistics gathered by sort_scatter4_kernel for the fixed-point eligibility test of the forward kernel
-// word of the tile scan region's header used as the persistent pullback kernel's work counter
-constexpr int kWorkCounter = 8;
-
-// Walks the (up to 27) sub-lists of a tile as one sequence, two entries ahead: index e of the concatenation -> sorted
-// point index.  `slot` only moves forward because e grows.
+// Walks the compact sub-list table of an item as one sequence: index e of the concatenation -> sorted point index.
 struct EntryCursor {
-    const Ranges* rg;
+    const ItemMeta* m;
     const uint32_t* entries;
     int slot;
+    uint32_t bound, base;
+    __device__ __forceinline__ void init(const ItemMeta* meta, const uint32_t* en) {
+        m = meta; entries = en; slot = 0;
+        bound = meta->end[0];
+        base = meta->base[0];
+    }
     __device__ __forceinline__ uint32_t fetch(uint32_t e) {
-        while (e >= rg->pref[slot + 1]) ++slot;
-        return __ldg(entries + rg->start[slot] + (e - rg->pref[slot]));
+        if (e >= bound) {
+            do { ++slot; bound = m->end[slot]; } while (e >= bound);
+            base = m->base[slot];
+        }
+        return __ldg(entries + (uint32_t)(base + e));       // 32-bit sum: base may have wrapped below zero
     }
 };
 
-__device__ __forceinline__ long long block_sum_i64(long long v, long long* scratch /* [kThreads / 32] */) {
+__device__ __forceinline__ long long consumer_sum_i64(long long v, long long* scratch /* [kConsumers / 32] */) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    __syncthreads();
+    bar_sync_consumers();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    __syncthreads();
+    bar_sync_consumers();
     long long t = 0;
 #pragma unroll
-    for (int i = 0; i < kThreads / 32; ++i) t += scratch[i];
+    for (int i = 0; i < kConsumers / 32; ++i) t += scratch[i];
     return t;
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// 5a. forward tile kernel: CTA = (pose, tile); accumulate in shared memory; one store per output cell
-//
-// Float32 accumulates in FIXED POINT on the native 32-bit shared-memory reduction (ATOMS.ADD without return: the float
-// atomicAdd is an LDS + ATOMS.CAST.SPIN loop on sm_100a and made this kernel issue 470 instructions per warp-entry,
-// profiles/ncu_r02_b_cfg3_summary.txt).  Same scheme as the 2-d kernels (dpr_forward_fast.cuh): a contribution
-// w * out_weight * point_weight = w * pw' * A (pw' = point_weight * 2^-em in [0, 1), A = out_weight * 2^em) is added as the
-// integer rint(w * pw' * Q), 2^(F-1) < Q <= 2^F <= 2^22, produced without a conversion (a product with the subnormal whose
-// bit pattern is Q is rounded to exactly that integer); the flush multiplies by A / Q.  A wrapped cell is detected exactly
-// by a mass checksum and the tile is then redone with float atomics, as it is for poses / weights that are not eligible
-// (non-positive out_weight, negative or non-finite point weights, dynamic range above 64).
-// ---------------------------------------------------------------------------------------------------------
-template <typename T, int N_IN>
-__global__ void __launch_bounds__(kThreads) fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ entries,
-                                                              const uint32_t* __restrict__ cnt, const T* __restrict__ rotation,
-                                                              const T* __restrict__ translation, const T* __restrict__ background,
-                                                              const T* __restrict__ out_weight, T* __restrict__ out,
-                                                              Grid<T, 3> grid, TileGeom tg, int64_t b0,
-                                                              const uint32_t* __restrict__ pw_stats, int64_t P, int fixed_bits) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* tile = reinterpret_cast<T*>(smem_raw);
-    __shared__ Ranges rg;
-    __shared__ long long scratch[kThreads / 32];
-    const int bl = blockIdx.x / tg.n_tiles;
-    const int t = blockIdx.x % tg.n_tiles;
-    const int tx = t % tg.nt[0], ty = (t / tg.nt[0]) % tg.nt[1], tz = t / (tg.nt[0] * tg.nt[1]);
-    const int64_t b = b0 + bl;
-    build_ranges(rg, cnt, tg, bl, tx, ty, tz);
-    constexpr int VEC = 16 / sizeof(T);
-    struct alignas(16) Pack { T v[VEC]; };
-    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
-    const T bg = background ? __ldg(background + b) : T(0);
-    T* __restrict__ img = out + b * grid.cells;
-    const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0;
-    __syncthreads();
-    const uint32_t total = rg.pref[64];
-
-    // stores `value(cell) + bg` for every cell of the tile that lies inside the volume; returns this thread's part of
-    // the integer cell sum (fixed-point mode)
-    auto flush = [&](bool fixed, float inv_q, bool empty) -> long long {
-        long long cells = 0;
-        for (int i = threadIdx.x; i < kTileCells / VEC; i += kThreads) {
-            const int x4 = (i % (TX / VEC)) * VEC, y = (i / (TX / VEC)) % TY, z = i / ((TX / VEC) * TY);
-            const int gx = ox + x4, gy = oy + y, gz = oz + z;
-            Pack pk;
-            if (empty) {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) pk.v[k] = bg;
-            } else {
-                pk = reinterpret_cast<const Pack*>(tile)[i];
-                if constexpr (sizeof(T) == 4) {
-                    if (fixed) {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) {
-                            const uint32_t u = __float_as_uint(pk.v[k]);
-                            cells += u;
-                            pk.v[k] = (float)u * inv_q;
-                        }
-                    }
-                }
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) pk.v[k] += bg;
-            }
-            if (gx >= grid.g[0] || gy >= grid.g[1] || gz >= grid.g[2]) continue;
-            T* dst = img + ((int64_t)gz * grid.g[1] + gy) * grid.g[0] + gx;
-            if (vec_ok && gx + VEC <= grid.g[0]) {
-                __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(&pk));
-            } else {
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) if (gx + k < grid.g[0]) dst[k] = pk.v[k];
-            }
-        }
-        return cells;
-    };
-    if (total == 0) {            // nothing lands here: the tile is the background (src/raster.jl:27)
-        flush(false, 0.f, true);
-        return;
+// Thread <-> tile cell mapping of the flush / tile sums: 16-byte piece r (r = 0 .. kPieces-1) of consumer thread tid is
+// (x4, y, z0 + r * kZStep) with everything but z fixed per thread - no division in the loops.
+template <typename T>
+struct CellMap {
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr int PX = TX / VEC;                              // pieces per row
+    static constexpr int kPieces = kTileCells / VEC / kConsumers;    // per thread
+    static constexpr int kZStep = kConsumers / (PX * TY);            // z advance per r
+    static_assert(kConsumers % (PX * TY) == 0 && kPieces * kZStep == TZ, "tile / CTA shape mismatch");
+    int x4, y, z0;
+    __device__ __forceinline__ CellMap() {
+        const int tid = threadIdx.x;
+        x4 = (tid % PX) * VEC;
+        y = (tid / PX) % TY;
+        z0 = tid / (PX * TY);
     }
-    auto zero_tile = [&]() {
-        for (int i = threadIdx.x; i < kTileCells / VEC; i += kThreads) {
-            Pack z;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
-            reinterpret_cast<Pack*>(tile)[i] = z;
-        }
-    };
-    zero_tile();
-    Pose<T, N_IN, 3> pose;
-    load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b);
+};
 
-    // ---- fixed-point eligibility and scale (uniform over the CTA) ---------------------------------------------
-    bool fixed = false;
-    float wq_den = 0.f, inv_q = 0.f, pw_scale = 1.f;
-    if constexpr (sizeof(T) == 4) {
-        bool ok = pose.ow > 0.f && fixed_bits > 0;
-        int em = 0;
-        if (pw_stats) {
-            const float wmax = __uint_as_float(__ldg(pw_stats + kStatMaxBits));
-            const float wmean = __uint_as_float(__ldg(pw_stats + kStatSum)) / (float)P;
-            ok = ok && __ldg(pw_stats + kStatBad) == 0u && wmax > 0.f && wmax < 3e38f && wmax <= 64.f * wmean;
-            if (ok) frexpf(wmax, &em);
-        }
-        const float A = ldexpf((float)pose.ow, em);
-        ok = ok && A > 1e-30f && A < 1e30f;
-        if (ok) {
-            int e;
-            frexpf(A, &e);                                        // A < 2^e
-            const float Q = rintf(ldexpf(A, fixed_bits - e));     // 2^(F-1) <= Q <= 2^F <= 2^22
-            wq_den = __int_as_float((int)Q);
-            inv_q = A / Q;
-            pw_scale = ldexpf(1.f, -em);
-            fixed = true;
-        }
-    }
-    __syncthreads();
+// the metadata ring (two batches), shared by both kernels
+struct MetaRing {
+    ItemMeta items[2 * kBatch];
+    uint64_t full[2], empty[2];     // mbarriers: batch published (count 1) / batch consumed (count = consumer warps)
+};
+__device__ __forceinline__ const ItemMeta& ring_item(const MetaRing& ring, int g) {
+    return ring.items[((g / kBatch) & 1) * kBatch + g % kBatch];
+}
+__device__ __forceinline__ void ring_wait_batch(MetaRing& ring, int batch) {
+    mbar_wait(&ring.full[batch & 1], (uint32_t)((batch >> 1) & 1));
+}
 
-    long long mass = 0;
-    // one pass over the tile's entries; FIXED selects the accumulation mode at compile time
-    auto accumulate = [&](auto fixed_tag) {
-        constexpr bool FIXED = decltype(fixed_tag)::value;
-        EntryCursor cur{&rg, entries, 0};
-        uint32_t e = threadIdx.x;
-        uint32_t idx_a = e < total ? cur.fetch(e) : 0u;
-        uint32_t idx_b = e + kThreads < total ? cur.fetch(e + kThreads) : 0u;
-        Pt4<T> qn = pts4[idx_a];
-        const uint32_t tile_s = smem_u32(tile);
-        for (; e < total; e += kThreads) {
-            const Pt4<T> q = qn;
-            idx_a = idx_b;
-            if (e + kThreads < total) qn = pts4[idx_a];
-            if (e + 2 * kThreads < total) idx_b = cur.fetch(e + 2 * kThreads);
-            T x[N_IN];
-            load_xyz<T, N_IN>(x, q);
-            int i0[3];
-            T dl[3], du[3];
-            if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;      // cannot happen: binned with the same arithmetic
-#pragma unroll
-            for (int k = 0; k < 3; ++k) du[k] = T(1) - dl[k];
-            const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
-            // corner values in bit order (x = bit 0): w_c * out_weight * point_weight (src/raster.jl:51,63,104-106), or its
-            // fixed-point image
-            T v[8];
-            if constexpr (FIXED) {
-                const float wq = wq_den * ((float)q.w * pw_scale);
-                const float az[2] = {(float)du[2] * wq, (float)dl[2] * wq};
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = T(((c & 1) ? (float)dl[0] : (float)du[0]) * (((c & 2) ? (float)dl[1] : (float)du[1]) * az[c >> 2]));
-            } else {
-                const T weight = pose.ow * q.w;
-#pragma unroll
-                for (int c = 0; c < 8; ++c) v[c] = corner_weight<T, 3>(c, dl, du) * weight;
-            }
-            const bool interior = (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) && (unsigned)lz < (unsigned)(TZ - 1) &&
-                                  i0[0] + 1 < grid.g[0] && i0[1] + 1 < grid.g[1] && i0[2] + 1 < grid.g[2];
-            const int off = (lz * TY + ly) * TX + lx;
-            if (interior) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int o = off + (c & 1) + ((c >> 1) & 1) * TX + ((c >> 2) & 1) * TX * TY;
-                    if constexpr (FIXED) {
-                        const uint32_t qv = __float_as_uint((float)v[c]);
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "r"(qv) : "memory");
-                        mass += qv;
-                    } else {
-                        atomicAdd(tile + o, v[c]);
-                    }
-                }
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
-                    // inside this CTA's tile and inside the grid (per-corner bounds rule, src/raster.jl:62)
-                    const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ &&
-                                    ox + cx < grid.g[0] && oy + cy < grid.g[1] && oz + cz < grid.g[2];
-                    if (!in) continue;
-                    const int o = (cz * TY + cy) * TX + cx;
-                    if constexpr (FIXED) {
-                        const uint32_t qv = __float_as_uint((float)v[c]);
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "r"(qv) : "memory");
-                        mass += qv;
-                    } else {
-                        atomicAdd(tile + o, v[c]);
-                    }
-                }
-            }
-        }
-    };
-    if constexpr (sizeof(T) == 4) {
-        if (fixed) {
-            accumulate(std::true_type{});
-            __syncthreads();
-            // optimistic flush; a wrapped 32-bit cell shows as (sum of cells) != (sum of contributions), exactly
-            const long long cells = flush(true, inv_q, false);
-            const long long diff = block_sum_i64(cells - mass, scratch);
-            if (diff == 0) return;
-            zero_tile();
-            __syncthreads();
-        }
+// The metadata producer warp: batch k + 1 is published as soon as the consumers have released batch k - 1, i.e. a whole
+// batch ahead of its first use; the ticket of batch k + 2 and the range loads of batch k + 1 are in flight meanwhile.
+__device__ __forceinline__ void produce_metadata(MetaRing& ring, const uint32_t* __restrict__ cnt, const TileGeom& tg, int n_work,
+                                                 uint32_t* __restrict__ work_counter) {
+    const int lane = threadIdx.x & 31;
+    int base_cur = 0, base_next = 0;
+    if (lane == 0) { base_cur = (int)atomicAdd(work_counter, (uint32_t)kBatch); base_next = (int)atomicAdd(work_counter, (uint32_t)kBatch); }
+    base_cur = __shfl_sync(0xffffffffu, base_cur, 0);
+    base_next = __shfl_sync(0xffffffffu, base_next, 0);
+    ItemMeta it;
+    MetaLoad ml;
+    decode_work(it, base_cur + lane, tg);                    // batch 0
+    meta_issue(ml, it, lane < kBatch && it.w < n_work, cnt, tg);
+    if (lane < kBatch) meta_finish(ring.items[lane], it, ml);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&ring.full[0]);
+    for (int k = 0;; ++k) {
+        if (base_cur >= n_work) break;                       // batch k ends the work: the consumers stop inside it
+        int base_next2 = 0;
+        if (lane == 0) base_next2 = (int)atomicAdd(work_counter, (uint32_t)kBatch);        // batch k + 2, used after this batch
+        decode_work(it, base_next + lane, tg);
+        meta_issue(ml, it, lane < kBatch && it.w < n_work, cnt, tg);
+        if (k + 1 >= 2) mbar_wait(&ring.empty[(k + 1) & 1], (uint32_t)((((k + 1) >> 1) - 1) & 1));   // batch k - 1 consumed
+        if (lane < kBatch) meta_finish(ring.items[((k + 1) & 1) * kBatch + lane], it, ml);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ring.full[(k + 1) & 1]);
+        base_cur = base_next;
+        base_next = __shfl_sync(0xffffffffu, base_next2, 0);
     }
-    accumulate(std::false_type{});
-    __syncthreads();
-    flush(false, 0.f, false);
+}
+
+// Consumer-side look-ahead across items.  Most tiles hold only a few entries per thread, so the dependent loads
+// (entry -> point) at the start of every item were exposed (profiles/ncu_r02_e_cfg3_summary.txt: a quarter of the stall
+// samples): every consumer thread therefore keeps the index of ITS first entry (e = tid) of item g + 2 and the point of
+// its first entry of item g + 1 in flight while it works on item g.
+constexpr int kLaIdx = 3, kLaPt = 1;
+template <typename T>
+struct Lookahead {
+    uint32_t idx[kLaIdx];      // before item g: first entry of this thread in items g .. g + 3 (0 when it has none)
+    Pt4<T> q[kLaPt];           // points of idx[0], idx[1]
+    __device__ __forceinline__ void init(const MetaRing& ring, int n_work, const uint32_t* __restrict__ entries, const Pt4<T>* __restrict__ pts4);
+    // take item g's first entry; item g + 2's point and item g + 4's index take off
+    __device__ __forceinline__ void rotate(MetaRing& ring, int g, int n_work, const uint32_t* __restrict__ entries,
+                                           const Pt4<T>* __restrict__ pts4, uint32_t& idx_first, Pt4<T>& q_first);
+};
+__device__ __forceinline__ uint32_t first_entry(const ItemMeta& m, int n_work, const uint32_t* __restrict__ entries) {
+    uint32_t idx = 0;
+    if (m.w < n_work && threadIdx.x < m.total) {
+        int s = 0;
+        while (threadIdx.x >= m.end[s]) ++s;
+        idx = __ldg(entries + (uint32_t)(m.base[s] + threadIdx.x));
+    }
+    return idx;
+}
+template <typename T>
+__device__ __forceinline__ void Lookahead<T>::init(const MetaRing& ring, int n_work, const uint32_t* __restrict__ entries,
+                                                    const Pt4<T>* __restrict__ pts4) {
+#pragma unroll
+    for (int k = 0; k < kLaIdx; ++k) idx[k] = first_entry(ring_item(ring, k), n_work, entries);      // kLaIdx <= kBatch: all in batch 0
+#pragma unroll
+    for (int k = 0; k < kLaPt; ++k) q[k] = pts4[idx[k]];
+}
+template <typename T>
+__device__ __forceinline__ void Lookahead<T>::rotate(MetaRing& ring, int g, int n_work, const uint32_t* __restrict__ entries,
+                                                      const Pt4<T>* __restrict__ pts4, uint32_t& idx_first, Pt4<T>& q_first) {
+    idx_first = idx[0];
+    q_first = q[0];
+#pragma unroll
+    for (int k = 0; k + 1 < kLaIdx; ++k) idx[k] = idx[k + 1];
+#pragma unroll
+    for (int k = 0; k + 1 < kLaPt; ++k) q[k] = q[k + 1];
+    q[kLaPt - 1] = pts4[idx[kLaPt - 1]];
+    if ((g + kLaIdx) % kBatch == 0) ring_wait_batch(ring, (g + kLaIdx) / kBatch);       // published a batch ahead: no stall in steady state
+    idx[kLaIdx - 1] = first_entry(ring_item(ring, g + kLaIdx), n_work, entries);
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 5b. pullback tile kernel
+// 5a. forward: accumulate in shared memory, one store per output cell (src/raster.jl:27,36-66)
+//
+// Float32 accumulates in FIXED POINT on the native 32-bit shared-memory reduction (ATOMS.ADD without return: the float
+// atomicAdd is an LDS + ATOMS.CAST.SPIN loop on sm_100a and made the first version issue 470 instructions per warp-entry).
+// Same scheme as the 2-d kernels (dpr_forward_fast.cuh): a contribution w * out_weight * point_weight = w * pw' * A
+// (pw' = point_weight * 2^-em in [0, 1), A = out_weight * 2^em) is added as the integer rint(w * pw' * Q),
+// 2^(F-1) < Q <= 2^F <= 2^22, produced without a conversion (a product with the subnormal whose bit pattern is Q is
+// rounded to exactly that integer); the flush multiplies by A / Q.  A tile with fewer than 2^(32-F) entries cannot wrap a
+// 32-bit cell; heavier tiles carry a mass checksum that detects a wrapped cell exactly, and the tile is then redone with
+// float atomics, as it is for poses / weights that are not eligible (non-positive out_weight, negative or non-finite
+// point weights, dynamic range above 64).
+// The tile rows are padded by one 16-byte piece and the planes by two: spatially sorted entries put the 32 lanes of a warp
+// into a blob a few cells wide, and with a dense 32-float pitch the bank would depend on x only (6 wavefronts per atomic in
+// the first version).  The tile is zero when an item starts: the flush reads each cell once, stores it, writes the zero back.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+struct FwdTile {
+    static constexpr int VEC = 16 / sizeof(T);
+    static constexpr int PITCH = TX + VEC;                  // elements per row
+    static constexpr int PLANE = TY * PITCH + 2 * VEC;      // elements per z-plane
+    static constexpr int SIZE = TZ * PLANE;                 // elements
+};
+
+template <typename T, int N_IN>
+__global__ void __launch_bounds__(kCtaThreads, sizeof(T) == 4 ? 4 : 2)
+fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt,
+                  const T* __restrict__ rotation, const T* __restrict__ translation, const T* __restrict__ background,
+                  const T* __restrict__ out_weight, T* __restrict__ out, Grid<T, 3> grid, TileGeom tg, int64_t b0, int n_work,
+                  uint32_t* __restrict__ work_counter, const uint32_t* __restrict__ pw_stats, int64_t P, int fixed_bits) {
+    using CM = CellMap<T>;
+    using FT = FwdTile<T>;
+    constexpr int VEC = CM::VEC;
+    struct alignas(16) Pack { T v[VEC]; };
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    __shared__ __align__(16) MetaRing ring;
+    __shared__ long long scratch[kConsumers / 32];
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int k = 0; k < 2; ++k) { mbar_init(&ring.full[k], 1); mbar_init(&ring.empty[k], kConsumers / 32); }
+        mbar_fence_init();
+    }
+    for (int i = threadIdx.x; i < FT::SIZE / VEC; i += kCtaThreads) {
+        Pack z;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
+        reinterpret_cast<Pack*>(tile)[i] = z;
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= kConsumers) {
+        produce_metadata(ring, cnt, tg, n_work, work_counter);          // ================= producer warp =================
+        return;
+    }
+
+    // ================= consumer warps =================
+    const CM cm;
+    const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0;
+    const int64_t plane = (int64_t)grid.g[0] * grid.g[1];
+    T* const my_cells = tile + (cm.z0 * FT::PLANE + cm.y * FT::PITCH + cm.x4);      // + r * kZStep * PLANE
+
+    // fixed-point statistics of the point weights (uniform, once)
+    bool pw_ok = true;
+    int em = 0;
+    if constexpr (sizeof(T) == 4) {
+        if (pw_stats) {
+            const float wmax = __uint_as_float(__ldg(pw_stats + kStatMaxBits));
+            const float wmean = __uint_as_float(__ldg(pw_stats + kStatSum)) / (float)P;
+            pw_ok = __ldg(pw_stats + kStatBad) == 0u && wmax > 0.f && wmax < 3e38f && wmax <= 64.f * wmean;
+            if (pw_ok) frexpf(wmax, &em);
+        }
+    }
+    const float pw_scale = ldexpf(1.f, -em);
+
+    int cur_bl = -1;
+    Pose<T, N_IN, 3> pose;
+    T bg = T(0);
+    bool fixed_pose = false;
+    float wq_den = 0.f, inv_q = 0.f;
+
+    ring_wait_batch(ring, 0);
+    Lookahead<T> la;
+    la.init(ring, n_work, entries, pts4);
+    for (int g = 0;; ++g) {
+        const int batch = g / kBatch, j = g % kBatch;
+        const ItemMeta& m = ring_item(ring, g);
+        if (m.w >= n_work) break;
+        uint32_t idx_first;
+        Pt4<T> q_first;
+        la.rotate(ring, g, n_work, entries, pts4, idx_first, q_first);
+        if (m.bl != cur_bl) {          // pose parameters and fixed-point scale (uniform over the CTA)
+            cur_bl = m.bl;
+            const int64_t b = b0 + m.bl;
+            load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b);
+            bg = background ? __ldg(background + b) : T(0);
+            fixed_pose = false;
+            if constexpr (sizeof(T) == 4) {
+                bool ok = pw_ok && pose.ow > 0.f && fixed_bits > 0;
+                const float A = ldexpf((float)pose.ow, em);
+                ok = ok && A > 1e-30f && A < 1e30f;
+                if (ok) {
+                    int e;
+                    frexpf(A, &e);                                        // A < 2^e
+                    const float Q = rintf(ldexpf(A, fixed_bits - e));     // 2^(F-1) <= Q <= 2^F <= 2^22
+                    wq_den = __int_as_float((int)Q);
+                    inv_q = A / Q;
+                    fixed_pose = true;
+                }
+            }
+        }
+        const uint32_t total = m.total;
+        const int ox = m.tx * TX, oy = m.ty * TY, oz = m.tz * TZ;
+        T* __restrict__ dst0 = out + (b0 + m.bl) * grid.cells + ((int64_t)(oz + cm.z0) * grid.g[1] + (oy + cm.y)) * grid.g[0] + (ox + cm.x4);
+        const bool col_ok = ox + cm.x4 < grid.g[0] && oy + cm.y < grid.g[1];
+        const bool full_vec = vec_ok && ox + cm.x4 + VEC <= grid.g[0];
+        const int z_lim = grid.g[2] - oz - cm.z0;            // piece r is inside the volume iff r * kZStep < z_lim
+
+        // stores value(cell) + bg for this thread's cells inside the volume and writes the zero back.
+        // MODE 0: background only (no shared-memory access); 1: float cells; 2: fixed-point cells; 3: fixed point + cell sum
+        auto flush = [&](auto mode_tag) -> long long {
+            constexpr int MODE = decltype(mode_tag)::value;
+            unsigned long long cells = 0;
+            T* dst = dst0;
+#pragma unroll
+            for (int r = 0; r < CM::kPieces; ++r, dst += CM::kZStep * plane) {
+                Pack pk;
+                if constexpr (MODE == 0) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) pk.v[k] = bg;
+                } else {
+                    Pack* cell = reinterpret_cast<Pack*>(my_cells + r * CM::kZStep * FT::PLANE);
+                    pk = *cell;
+                    Pack z;
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
+                    *cell = z;
+                    if constexpr (MODE >= 2 && sizeof(T) == 4) {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) {
+                            const uint32_t u = __float_as_uint(pk.v[k]);
+                            if constexpr (MODE == 3) cells += u;
+                            pk.v[k] = fmaf((float)u, inv_q, bg);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) pk.v[k] += bg;
+                    }
+                }
+                if (!col_ok || r * CM::kZStep >= z_lim) continue;
+                if (full_vec) {
+                    __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(&pk));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) if (ox + cm.x4 + k < grid.g[0]) dst[k] = pk.v[k];
+                }
+            }
+            return (long long)cells;
+        };
+
+        if (total == 0) {            // nothing lands here: the tile is the background (src/raster.jl:27)
+            flush(std::integral_constant<int, 0>{});
+        } else {
+            long long mass = 0;
+            // one pass over the item's entries.  FIXED: accumulation mode.  Entries below n_int are the tile's own pattern-0
+            // list, whose stencils lie inside the tile (only the volume's faces can still clip them: the checked path)
+            const uint32_t n_int = m.n_interior;
+            auto accumulate = [&](auto fixed_tag) {
+                constexpr bool FIXED = decltype(fixed_tag)::value;
+                uint32_t e = threadIdx.x;
+                if (e >= total) return;
+                EntryCursor cur;
+                cur.init(&m, entries);
+                // software pipeline over this thread's entries: index three ahead, point two ahead
+                uint32_t i1 = e + kConsumers < total ? cur.fetch(e + kConsumers) : 0u;
+                uint32_t i2 = e + 2 * kConsumers < total ? cur.fetch(e + 2 * kConsumers) : 0u;
+                Pt4<T> p0 = q_first, p1 = pts4[i1];
+                const uint32_t tile_s = smem_u32(tile);
+                for (; e < total; e += kConsumers) {
+                    const Pt4<T> q = p0;
+                    p0 = p1;
+                    i1 = i2;
+                    if (e + 2 * kConsumers < total) p1 = pts4[i1];
+                    if (e + 3 * kConsumers < total) i2 = cur.fetch(e + 3 * kConsumers);
+                    T x[N_IN];
+                    load_xyz<T, N_IN>(x, q);
+                    int i0[3];
+                    T dl[3], du[3];
+                    if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;      // cannot happen: binned with the same arithmetic
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) du[k] = T(1) - dl[k];
+                    const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
+                    // corner values in bit order (x = bit 0): w_c * out_weight * point_weight (src/raster.jl:51,63,104-106),
+                    // or its fixed-point image
+                    T v[8];
+                    if constexpr (FIXED) {
+                        const float wq = wq_den * ((float)q.w * pw_scale);
+                        const float az[2] = {(float)du[2] * wq, (float)dl[2] * wq};
+                        const float byz[4] = {(float)du[1] * az[0], (float)dl[1] * az[0], (float)du[1] * az[1], (float)dl[1] * az[1]};
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] = T(((c & 1) ? (float)dl[0] : (float)du[0]) * byz[c >> 1]);
+                    } else {
+                        const T weight = pose.ow * q.w;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) v[c] = corner_weight<T, 3>(c, dl, du) * weight;
+                    }
+                    uint32_t msum = 0;
+                    auto add = [&](int o, T val) {
+                        if constexpr (FIXED) {
+                            const uint32_t qv = __float_as_uint((float)val);
+                            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "r"(qv) : "memory");
+                            msum += qv;
+                        } else {
+                            atomicAdd(tile + o, val);
+                        }
+                    };
+                    const bool inside = e < n_int && (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) &&
+                                        (unsigned)lz < (unsigned)(TZ - 1) && i0[0] + 1 < grid.g[0] && i0[1] + 1 < grid.g[1] && i0[2] + 1 < grid.g[2];
+                    if (inside) {
+                        const int off = lz * FT::PLANE + ly * FT::PITCH + lx;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) add(off + (c & 1) + ((c >> 1) & 1) * FT::PITCH + ((c >> 2) & 1) * FT::PLANE, v[c]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) {
+                            const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
+                            // inside this item's tile and inside the grid (per-corner bounds rule, src/raster.jl:62)
+                            const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ &&
+                                            ox + cx < grid.g[0] && oy + cy < grid.g[1] && oz + cz < grid.g[2];
+                            if (in) add(cz * FT::PLANE + cy * FT::PITCH + cx, v[c]);
+                        }
+                    }
+                    mass += msum;       // 8 values below 2^22 each: no 32-bit overflow inside one entry
+                }
+            };
+            bool done = false;
+            if constexpr (sizeof(T) == 4) {
+                if (fixed_pose) {
+                    accumulate(std::true_type{});
+                    bar_sync_consumers();
+                    // a cell receives at most `total` contributions of at most 2^F: light tiles cannot wrap
+                    const bool can_wrap = ((unsigned long long)total << fixed_bits) >= (1ull << 32);
+                    done = true;
+                    if (!can_wrap) {
+                        flush(std::integral_constant<int, 2>{});
+                    } else {
+                        const long long cells = flush(std::integral_constant<int, 3>{});          // optimistic
+                        if (consumer_sum_i64(cells - mass, scratch) != 0) done = false;    // a wrapped cell: sums differ, exactly
+                    }
+                    bar_sync_consumers();                   // the tile is zero again
+                }
+            }
+            if (!done) {
+                accumulate(std::false_type{});
+                bar_sync_consumers();
+                flush(std::integral_constant<int, 1>{});
+                bar_sync_consumers();
+            }
+        }
+        if (j == kBatch - 1) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ring.empty[batch & 1]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// 5b. pullback (src/raster_pullback.jl:2-82 per pose; ext/DiffPointRasterisationCUDAExt.jl:19-210 is what it replaces)
+//
+// USE_TMA: the producer also fetches the ds_dout tile of every item with ONE 4-d tensor-map TMA copy
+// (cp.async.bulk.tensor, SASS UTMALDG; cells outside the volume arrive as zeros) into a kStages-deep shared-memory ring,
+// kStages - 1 items ahead of the consumers, signalled per stage on a full / empty mbarrier pair.
+//   (Round 1 had declared tensor-map TMA unusable on this pool - "illegal instruction".  The fault is a constraint, not a
+//    defect: the box must START on a 16-byte boundary in the innermost dimension (c0 * sizeof(T) % 16 == 0), and both
+//    round-1 probes used c0 = -10.  tools/probe_tma_tensor3.cu, profiles/tma_probe_r02.log.  Tile origins are multiples
+//    of TX = 32 cells here.)
+// !USE_TMA (rows that are not 16-byte multiples): the consumers load the tile cooperatively, synchronously.
+// Work items of one CTA increase, so the pose only moves forward: the 3 N_in + 4 per-pose sums and the d_background
+// partial (src/raster_pullback.jl:78: summed from the staged tile, zero outside the volume) stay in registers across items
+// and are block-reduced only when the pose changes.  The sample and its three derivatives come from the factorised
+// trilinear form (25 flops instead of ~150 for the corner-by-corner sums).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_tile4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
     asm volatile(
@@ -589,255 +819,84 @@ __device__ __forceinline__ void red_add4(Pt4<double>* addr, double a, double b, 
     atomicAdd(&addr->w, d);
 }
 
+constexpr int kStages = 2;
+
+constexpr int kPbThreads = kConsumers + 64;       // consumers + metadata producer warp + tile (TMA) producer warp
+
 template <typename T, int N_IN, bool USE_TMA>
-__global__ void __launch_bounds__(kThreads)
-pullback_tile3d_simple_kernel(const __grid_constant__ CUtensorMap map, const T* __restrict__ ds_dout, const Pt4<T>* __restrict__ pts4,
+__global__ void __launch_bounds__(kPbThreads, sizeof(T) == 4 ? 3 : 1)
+pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restrict__ ds_dout, const Pt4<T>* __restrict__ pts4,
                        const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt, const T* __restrict__ rotation,
                        const T* __restrict__ translation, const T* __restrict__ out_weight, Pt4<T>* __restrict__ acc4,
                        T* __restrict__ d_rotation, T* __restrict__ d_translation, T* __restrict__ d_background,
-                       T* __restrict__ d_out_weight, Grid<T, 3> grid, TileGeom tg, int64_t b0) {
+                       T* __restrict__ d_out_weight, Grid<T, 3> grid, TileGeom tg, int64_t b0, int n_work,
+                       uint32_t* __restrict__ work_counter) {
     constexpr int NR = 3 * N_IN, NV = NR + 3 + 1;     // d_rotation (col-major 3 x N_IN), d_translation, d_out_weight
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* tile = reinterpret_cast<T*>(smem_raw);
-    __shared__ Ranges rg;
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ T red[kThreads / 32][NV + 1];
-    const int bl = blockIdx.x / tg.n_tiles;
-    const int t = blockIdx.x % tg.n_tiles;
-    const int tx = t % tg.nt[0], ty = (t / tg.nt[0]) % tg.nt[1], tz = t / (tg.nt[0] * tg.nt[1]);
-    const int64_t b = b0 + bl;
-    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    constexpr int VEC = 16 / sizeof(T);
-    struct alignas(16) Pack { T v[VEC]; };
-
-    if (USE_TMA) {
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            mbar_fence_init();
-            mbar_arrive_expect_tx(&bar, (uint32_t)(kTileCells * sizeof(T)));
-            tma_load_tile4d(tile, &map, ox, oy, oz, (int)b, &bar);          // cells outside the volume arrive as zeros
-        }
-    } else {
-        const T* __restrict__ img = ds_dout + b * grid.cells;
-        const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) % 16) == 0;
-#pragma unroll 4
-        for (int i = threadIdx.x; i < kTileCells / VEC; i += kThreads) {
-            const int x4 = (i % (TX / VEC)) * VEC, y = (i / (TX / VEC)) % TY, z = i / ((TX / VEC) * TY);
-            const int gx = ox + x4, gy = oy + y, gz = oz + z;
-            Pack pk;
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) pk.v[k] = T(0);
-            if (gx < grid.g[0] && gy < grid.g[1] && gz < grid.g[2]) {
-                const T* src = img + ((int64_t)gz * grid.g[1] + gy) * grid.g[0] + gx;
-                if (vec_ok && gx + VEC <= grid.g[0]) {
-                    const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
-                    pk = *reinterpret_cast<const Pack*>(&q);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) if (gx + k < grid.g[0]) pk.v[k] = __ldg(src + k);
-                }
-            }
-            reinterpret_cast<Pack*>(tile)[i] = pk;
-        }
-    }
-    build_ranges(rg, cnt, tg, bl, tx, ty, tz);
-    __syncthreads();                       // ranges (and the mbarrier init / the cooperative tile load) visible
-    if (USE_TMA) mbar_wait(&bar, 0);
-
-    T acc[NV];
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = T(0);
-    T bg_part = T(0);
-    if (d_background) {                    // src/raster_pullback.jl:78 - from the staged tile (zero outside the volume)
-        for (int i = threadIdx.x; i < kTileCells / VEC; i += kThreads) {
-            const Pack pk = reinterpret_cast<const Pack*>(tile)[i];
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) bg_part += pk.v[k];
-        }
-    }
-    const uint32_t total = rg.pref[64];
-    if (total) {
-        Pose<T, N_IN, 3> pose;
-        load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b);
-        int slot = 0;
-        for (uint32_t e = threadIdx.x; e < total; e += kThreads) {
-            while (e >= rg.pref[slot + 1]) ++slot;
-            const uint32_t idx = __ldg(entries + rg.start[slot] + (e - rg.pref[slot]));
-            const Pt4<T> q = pts4[idx];
-            T x[N_IN];
-            load_xyz<T, N_IN>(x, q);
-            int i0[3];
-            T dl[3], du[3];
-            if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) du[k] = T(1) - dl[k];
-            const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
-            T s = T(0), gk[3] = {T(0), T(0), T(0)};
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
-                // corners of other tiles are that tile's CTA's job; corners outside the volume read the zero fill, which
-                // equals skipping them (src/raster_pullback.jl:51)
-                const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ;
-                const T G = in ? tile[(cz * TY + cy) * TX + cx] : T(0);
-                s += corner_weight<T, 3>(c, dl, du) * G;                                        // :55-58
-#pragma unroll
-                for (int n = 0; n < 3; ++n) {                                                    // :60-65, :150-160
-                    T iw = ((c >> n) & 1) ? T(1) : T(-1);
-#pragma unroll
-                    for (int m = 0; m < 3; ++m)
-                        if (m != n) iw *= ((c >> m) & 1) ? dl[m] : du[m];
-                    gk[n] += G * iw;
-                }
-            }
-            acc[NV - 1] += s * q.w;                           // d_out_weight,   src/raster_pullback.jl:57
-            const T f = pose.ow * q.w;                        // :60
-            T scaled[3];
-#pragma unroll
-            for (int n = 0; n < 3; ++n) {
-                scaled[n] = (f * gk[n]) * grid.scale[n];      // :67
-                acc[NR + n] += scaled[n];                     // d_translation, :68
-            }
-            T dpt[3] = {T(0), T(0), T(0)};
-#pragma unroll
-            for (int j = 0; j < N_IN; ++j) {
-                T d = T(0);
-#pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    acc[n + j * 3] += scaled[n] * x[j];       // d_rotation, :69
-                    d += pose.R[n][j] * scaled[n];            // R' * scaled, :70
-                }
-                dpt[j] = d;
-            }
-            // pose-sum of d_points (:71, :141) and d_point_weight (:58, :146): one 16-byte reduction into the packed,
-            // L2-resident buffer (sorted point order)
-            red_add4(acc4 + idx, dpt[0], dpt[1], dpt[2], s * pose.ow);
-        }
-    }
-    // per-pose sums of this CTA: warp shuffles, then one line of shared memory per warp, then one REDG per value
-#pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = warp_sum(acc[v]);
-    bg_part = warp_sum(bg_part);
-    if (lane == 0) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
-        red[warp][NV] = bg_part;
-    }
-    __syncthreads();
-    if (threadIdx.x <= NV) {
-        const int v = threadIdx.x;
-        T r = T(0);
-#pragma unroll
-        for (int w = 0; w < kThreads / 32; ++w) r += red[w][v];
-        if (v == NV) { if (d_background) red_add(d_background + b, r); }
-        else if (r != T(0)) {
-            if (v < NR) red_add(d_rotation + b * NR + v, r);
-            else if (v < NR + 3) red_add(d_translation + b * 3 + (v - NR), r);
-            else if (d_out_weight) red_add(d_out_weight + b, r);
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// 5c. pullback tile kernel, persistent: the production path when rows are 16-byte multiples.
-//
-// The one-CTA-per-tile kernel above spends 37 % of its stall samples waiting for its own tile load (profiles/
-// ncu_r02_b_cfg3_summary.txt: the loads are synchronous and only three CTAs fit an SM) and pays a block reduction per
-// tile.  Here a CTA keeps pulling (pose, tile) tickets from a global counter; the ds_dout tile of the NEXT ticket is
-// streamed into the other half of a two-stage shared-memory ring with 16-byte cp.async (LDGSTS, zero-filled outside the
-// volume) and its sub-list ranges are fetched by warp 0 while the current tile is processed; tickets are taken two ahead
-// so the atomic's latency is hidden too.  Tickets of one CTA increase, so the pose only moves forward: the 3 N_in + 5
-// per-pose sums (and the d_background partial) stay in registers across tiles and are block-reduced only when the pose
-// changes.  The sample and its three derivatives come from the factorised trilinear form (25 flops instead of ~150).
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16_zfill(uint32_t dst, const void* src, bool valid) {
-    const int bytes = valid ? 16 : 0;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <typename T, int N_IN>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 3 : 1)
-pullback_tile3d_kernel(const T* __restrict__ ds_dout, const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ entries,
-                       const uint32_t* __restrict__ cnt, const T* __restrict__ rotation, const T* __restrict__ translation,
-                       const T* __restrict__ out_weight, Pt4<T>* __restrict__ acc4, T* __restrict__ d_rotation,
-                       T* __restrict__ d_translation, T* __restrict__ d_background, T* __restrict__ d_out_weight,
-                       Grid<T, 3> grid, TileGeom tg, int64_t b0, int n_work, uint32_t* __restrict__ work_counter) {
-    constexpr int NR = 3 * N_IN, NV = NR + 3 + 1;     // d_rotation (col-major 3 x N_IN), d_translation, d_out_weight
-    constexpr int VEC = 16 / sizeof(T);
+    using CM = CellMap<T>;
+    constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* const ring = reinterpret_cast<T*>(smem_raw);       // two stages of kTileCells
-    __shared__ Ranges rg[2];
-    __shared__ T red[kThreads / 32][NV + 1];
-    __shared__ int s_ticket[4];
+    T* const stages = reinterpret_cast<T*>(smem_raw);     // kStages (TMA) or 1 (cooperative loads) tiles of kTileCells
+    __shared__ __align__(16) MetaRing ring;
+    __shared__ __align__(8) uint64_t tile_full[kStages], tile_empty[kStages];
+    __shared__ T red[kConsumers / 32][NV + 1];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    auto tile_coords = [&](int w, int& bl, int& tx, int& ty, int& tz) {
-        bl = w / tg.n_tiles;
-        const int t = w % tg.n_tiles;
-        tx = t % tg.nt[0]; ty = (t / tg.nt[0]) % tg.nt[1]; tz = t / (tg.nt[0] * tg.nt[1]);
-    };
-    // asynchronous copy of work item w's ds_dout tile into ring stage st (16-byte pieces; zero outside the volume)
-    auto issue_tile = [&](int w, int st) {
-        int bl, tx, ty, tz;
-        tile_coords(w, bl, tx, ty, tz);
-        const T* __restrict__ img = ds_dout + (b0 + bl) * grid.cells;
-        const uint32_t dst0 = smem_u32(ring + (size_t)st * kTileCells);
-#pragma unroll
-        for (int r = 0; r < kTileCells / VEC / kThreads; ++r) {
-            const int i = r * kThreads + (int)threadIdx.x;
-            const int x4 = (i % (TX / VEC)) * VEC, y = (i / (TX / VEC)) % TY, z = i / ((TX / VEC) * TY);
-            const int gx = tx * TX + x4, gy = ty * TY + y, gz = tz * TZ + z;
-            const bool valid = gx < grid.g[0] && gy < grid.g[1] && gz < grid.g[2];      // rows are multiples of VEC: whole piece
-            const T* src = valid ? img + ((int64_t)gz * grid.g[1] + gy) * grid.g[0] + gx : ds_dout;
-            cp_async16_zfill(dst0 + (uint32_t)i * 16u, src, valid);
-        }
-    };
 
     if (threadIdx.x == 0) {
-        s_ticket[0] = (int)atomicAdd(work_counter, 1u);
-        s_ticket[1] = (int)atomicAdd(work_counter, 1u);
+        for (int k = 0; k < 2; ++k) { mbar_init(&ring.full[k], 1); mbar_init(&ring.empty[k], kConsumers / 32); }
+        for (int k = 0; k < kStages; ++k) { mbar_init(&tile_full[k], 1); mbar_init(&tile_empty[k], kConsumers / 32); }
+        mbar_fence_init();
     }
     __syncthreads();
-    int w_cur = s_ticket[0], w_next = s_ticket[1];
-    if (w_cur >= n_work) return;
-    int st = 0;
-    issue_tile(w_cur, 0);
-    cp_async_commit();
-    {
-        int bl, tx, ty, tz;
-        tile_coords(w_cur, bl, tx, ty, tz);
-        build_ranges(rg[0], cnt, tg, bl, tx, ty, tz);
+
+    if (threadIdx.x >= kConsumers + 32) {
+        // ================= tile producer warp: one tensor-map TMA copy per item, kStages - 1 items ahead =================
+        if (USE_TMA) {
+            for (int g = 0;; ++g) {
+                if (g % kBatch == 0) ring_wait_batch(ring, g / kBatch);
+                const ItemMeta& m = ring_item(ring, g);
+                if (m.w >= n_work) break;
+                const int stage = g % kStages;
+                if (g >= kStages) mbar_wait(&tile_empty[stage], (uint32_t)(((g / kStages) - 1) & 1));     // consumers released it
+                if (lane == 0) {
+                    mbar_arrive_expect_tx(&tile_full[stage], (uint32_t)(kTileCells * sizeof(T)));
+                    tma_load_tile4d(stages + (size_t)stage * kTileCells, &map, m.tx * TX, m.ty * TY, m.tz * TZ, (int)(b0 + m.bl), &tile_full[stage]);
+                }
+            }
+        }
+        return;
+    }
+    if (threadIdx.x >= kConsumers) {
+        produce_metadata(ring, cnt, tg, n_work, work_counter);          // ================= metadata producer warp =================
+        return;
     }
 
+    // ================= consumer warps =================
+    const CM cm;
     T acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = T(0);
     T bg_part = T(0);
     int cur_bl = -1;
     Pose<T, N_IN, 3> pose;
-    // block-reduce the per-pose sums of pose b0 + cur_bl and add them to the outputs (all threads call it)
+    // reduce the per-pose sums of pose b0 + cur_bl over the consumers and add them to the outputs (all consumers call it)
     auto flush_pose = [&]() {
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[v] = warp_sum(acc[v]);
         bg_part = warp_sum(bg_part);
-        __syncthreads();
+        bar_sync_consumers();
         if (lane == 0) {
 #pragma unroll
             for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
             red[warp][NV] = bg_part;
         }
-        __syncthreads();
+        bar_sync_consumers();
         if (threadIdx.x <= NV) {
             const int v = threadIdx.x;
             const int64_t b = b0 + cur_bl;
             T r = T(0);
 #pragma unroll
-            for (int w = 0; w < kThreads / 32; ++w) r += red[w][v];
+            for (int w = 0; w < kConsumers / 32; ++w) r += red[w][v];
             if (v == NV) { if (d_background) red_add(d_background + b, r); }
             else if (r != T(0)) {
                 if (v < NR) red_add(d_rotation + b * NR + v, r);
@@ -850,64 +909,93 @@ pullback_tile3d_kernel(const T* __restrict__ ds_dout, const Pt4<T>* __restrict__
         bg_part = T(0);
     };
 
-    for (int iter = 0;; ++iter) {
-        // the ticket after next: written to a slot that alternates per iteration, read after this iteration's last barrier
-        if (threadIdx.x == 0) s_ticket[2 + (iter & 1)] = (int)atomicAdd(work_counter, 1u);
-        if (w_next < n_work) issue_tile(w_next, st ^ 1);
-        cp_async_commit();
-        RangeLoad rl_next;
-        rl_next.s[0] = rl_next.s[1] = rl_next.e[0] = rl_next.e[1] = 0u;
-        if (w_next < n_work) {              // warp 0 issues the loads now and uses them after this tile's entries
-            int bl, tx, ty, tz;
-            tile_coords(w_next, bl, tx, ty, tz);
-            rl_next = ranges_issue(cnt, tg, bl, tx, ty, tz);
-        }
-        cp_async_wait<1>();                 // this thread's pieces of the current tile have landed
-        __syncthreads();                    // everyone's pieces + rg[st] visible
-
-        int bl, tx, ty, tz;
-        tile_coords(w_cur, bl, tx, ty, tz);
-        if (bl != cur_bl) {
+    ring_wait_batch(ring, 0);
+    Lookahead<T> la;
+    la.init(ring, n_work, entries, pts4);
+    for (int g = 0;; ++g) {
+        const int batch = g / kBatch, j = g % kBatch;
+        const ItemMeta& m = ring_item(ring, g);
+        if (m.w >= n_work) break;
+        uint32_t idx_first;
+        Pt4<T> q_first;
+        la.rotate(ring, g, n_work, entries, pts4, idx_first, q_first);
+        const int stage = USE_TMA ? g % kStages : 0;
+        if (m.bl != cur_bl) {
             if (cur_bl >= 0) flush_pose();
-            cur_bl = bl;
-            load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b0 + bl);
+            cur_bl = m.bl;
+            load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b0 + m.bl);
         }
-        const T* __restrict__ tile = ring + (size_t)st * kTileCells;
-        const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+        const int ox = m.tx * TX, oy = m.ty * TY, oz = m.tz * TZ;
+        T* __restrict__ tile = stages + (size_t)stage * kTileCells;
+        if (USE_TMA) {
+            mbar_wait(&tile_full[stage], (uint32_t)((g / kStages) & 1));      // the tile has landed
+        } else {
+            // cooperative synchronous load (any row length / alignment); zero outside the volume
+            bar_sync_consumers();                                             // everyone is done with the previous tile
+            const T* __restrict__ img = ds_dout + (b0 + m.bl) * grid.cells;
+            const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) % 16) == 0;
+#pragma unroll
+            for (int r = 0; r < CM::kPieces; ++r) {
+                const int gx = ox + cm.x4, gy = oy + cm.y, gz = oz + cm.z0 + r * CM::kZStep;
+                Pack pk;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) pk.v[k] = T(0);
+                if (gx < grid.g[0] && gy < grid.g[1] && gz < grid.g[2]) {
+                    const T* src = img + ((int64_t)gz * grid.g[1] + gy) * grid.g[0] + gx;
+                    if (vec_ok && gx + VEC <= grid.g[0]) {
+                        const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
+                        pk = *reinterpret_cast<const Pack*>(&q);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) if (gx + k < grid.g[0]) pk.v[k] = __ldg(src + k);
+                    }
+                }
+                reinterpret_cast<Pack*>(tile)[r * kConsumers + threadIdx.x] = pk;
+            }
+            bar_sync_consumers();
+        }
         if (d_background) {                 // src/raster_pullback.jl:78 - from the staged tile (zero outside the volume)
 #pragma unroll
-            for (int r = 0; r < kTileCells / VEC / kThreads; ++r) {
-                const Pack pk = reinterpret_cast<const Pack*>(tile)[r * kThreads + threadIdx.x];
+            for (int r = 0; r < CM::kPieces; ++r) {
+                const Pack pk = reinterpret_cast<const Pack*>(tile)[r * kConsumers + threadIdx.x];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) bg_part += pk.v[k];
             }
         }
-        const Ranges& rgc = rg[st];
-        const uint32_t total = rgc.pref[64];
-        if (total) {
-            EntryCursor cur{&rgc, entries, 0};
+        const uint32_t total = m.total;
+        // one pass over the item's entries; those below n_interior are the tile's own pattern-0 list (all eight corners on chip)
+        if (threadIdx.x < total) {
+            const uint32_t n_int = m.n_interior;
             uint32_t e = threadIdx.x;
-            uint32_t idx_a = e < total ? cur.fetch(e) : 0u;
-            uint32_t idx_b = e + kThreads < total ? cur.fetch(e + kThreads) : 0u;
-            Pt4<T> qn = pts4[idx_a];
-            for (; e < total; e += kThreads) {
-                const Pt4<T> q = qn;
-                const uint32_t idx = idx_a;
-                idx_a = idx_b;
-                if (e + kThreads < total) qn = pts4[idx_a];
-                if (e + 2 * kThreads < total) idx_b = cur.fetch(e + 2 * kThreads);
+            EntryCursor cur;
+            cur.init(&m, entries);
+            // software pipeline over this thread's entries: index three ahead, point two ahead
+            uint32_t i0 = idx_first;
+            uint32_t i1 = e + kConsumers < total ? cur.fetch(e + kConsumers) : 0u;
+            uint32_t i2 = e + 2 * kConsumers < total ? cur.fetch(e + 2 * kConsumers) : 0u;
+            uint32_t ip = i1;                                   // index of the point in p1
+            Pt4<T> p0 = q_first, p1 = pts4[i1];
+            for (; e < total; e += kConsumers) {
+                const Pt4<T> q = p0;
+                const uint32_t idx = i0;
+                p0 = p1;
+                i0 = ip;
+                i1 = i2;
+                ip = i1;
+                if (e + 2 * kConsumers < total) p1 = pts4[i1];
+                if (e + 3 * kConsumers < total) i2 = cur.fetch(e + 3 * kConsumers);
                 T x[N_IN];
                 load_xyz<T, N_IN>(x, q);
                 int i0[3];
                 T dl[3];
                 if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;
                 const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
-                // corner values in bit order (x = bit 0).  Corners of other tiles are that tile's CTA's job (everything is
+                // corner values in bit order (x = bit 0).  Corners of other tiles are that tile's item's job (everything is
                 // linear in G); corners outside the volume read the zero fill = skipped (src/raster_pullback.jl:51)
                 T G[8];
-                const bool interior = (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) && (unsigned)lz < (unsigned)(TZ - 1);
-                const int off = (lz * TY + ly) * TX + lx;
-                if (interior) {
+                const bool inside = e < n_int && (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) && (unsigned)lz < (unsigned)(TZ - 1);
+                if (inside) {
+                    const int off = (lz * TY + ly) * TX + lx;
 #pragma unroll
                     for (int c = 0; c < 8; ++c) G[c] = tile[off + (c & 1) + ((c >> 1) & 1) * TX + ((c >> 2) & 1) * TX * TY];
                 } else {
@@ -948,28 +1036,27 @@ pullback_tile3d_kernel(const T* __restrict__ ds_dout, const Pt4<T>* __restrict__
                 }
                 T dpt[3] = {T(0), T(0), T(0)};
 #pragma unroll
-                for (int j = 0; j < N_IN; ++j) {
+                for (int jj = 0; jj < N_IN; ++jj) {
                     T d = T(0);
 #pragma unroll
                     for (int n = 0; n < 3; ++n) {
-                        acc[n + j * 3] += scaled[n] * x[j];       // d_rotation, :69
-                        d += pose.R[n][j] * scaled[n];            // R' * scaled, :70
+                        acc[n + jj * 3] += scaled[n] * x[jj];     // d_rotation, :69
+                        d += pose.R[n][jj] * scaled[n];           // R' * scaled, :70
                     }
-                    dpt[j] = d;
+                    dpt[jj] = d;
                 }
                 // pose-sum of d_points (:71, :141) and d_point_weight (:58, :146): one 16-byte reduction into the packed,
                 // L2-resident buffer (sorted point order)
                 red_add4(acc4 + idx, dpt[0], dpt[1], dpt[2], s * pose.ow);
             }
         }
-        ranges_finish(rg[st ^ 1], rl_next);
-        __syncthreads();                    // stage st may be refilled; rg[st ^ 1] and the new ticket are visible
-        w_cur = w_next;
-        w_next = s_ticket[2 + (iter & 1)];
-        st ^= 1;
-        if (w_cur >= n_work) break;
+        __syncwarp();
+        if (lane == 0) {
+            if (USE_TMA) mbar_arrive(&tile_empty[stage]);           // this warp is done with the stage
+            if (j == kBatch - 1) mbar_arrive(&ring.empty[batch & 1]);
+        }
     }
-    flush_pose();
+    if (cur_bl >= 0) flush_pose();
 }
 
 // 6. packed, sorted-order gradients -> d_points (N_in, P) and d_point_weight (P) in the caller's point order
@@ -996,7 +1083,7 @@ struct Plan {
     TileGeom tg{};
     int64_t group = 0;             // poses binned per pass
     ScanRegion sort_scan, tile_scan;
-    size_t off_keys = 0, off_perm = 0, off_pts4 = 0, off_acc4 = 0, off_entries = 0, total = 0;
+    size_t off_keys = 0, off_perm = 0, off_pts4 = 0, off_acc4 = 0, off_entries = 0, off_tile_keys = 0, total = 0;
 };
 
 inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int sizeof_T, bool pullback) {
@@ -1022,7 +1109,7 @@ inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int s
     // pre-sort cells: ~4 points per cell, 2..6 bits per dimension (measured on B200, 1 M points: 2^15 cells make the
     // histogram and scatter atomics three times slower than 2^18 cells - same-address contention at L2)
     int bits = 2;
-    while (bits < 6 && ((int64_t)4 << (n_in * (bits + 1))) <= P) ++bits;
+    while (bits < 6 && ((int64_t)2 << (n_in * (bits + 1))) <= P) ++bits;
     pl.sort_bits = bits;
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };
     size_t o = 256;
@@ -1035,6 +1122,7 @@ inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int s
     pl.tile_scan = make_scan_region(o, group * n_tiles * 8);
     o = pl.tile_scan.off_ticket + pl.tile_scan.bytes;
     pl.off_entries = o; o = al(o + sizeof(uint32_t) * (size_t)(P * group));
+    pl.off_tile_keys = o; o = al(o + sizeof(uint32_t) * (size_t)(P * group));       // keys of pass 1, re-read by pass 2
     pl.total = o;
     pl.ok = true;
     return pl;
@@ -1078,16 +1166,17 @@ static int bin_poses(const T* rotation, const T* translation, const Grid<T, 3>& 
     const Pt4<T>* pts4 = reinterpret_cast<const Pt4<T>*>(ws + pl.off_pts4);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(ws + sr.off_data);
     uint32_t* entries = reinterpret_cast<uint32_t*>(ws + pl.off_entries);
+    uint32_t* tile_keys = reinterpret_cast<uint32_t*>(ws + pl.off_tile_keys);
     const dim3 gridDim3((unsigned)((P + 1023) / 1024), (unsigned)nb);
     {
         LaunchScope scope("tile3_bin_count", stream);
-        tile_bin_kernel<T, N_IN, false><<<gridDim3, 256, 0, stream>>>(pts4, (int)P, rotation, translation, grid, pl.tg, cnt, entries, b0);
+        tile_count_kernel<T, N_IN><<<gridDim3, 256, 0, stream>>>(pts4, (int)P, rotation, translation, grid, pl.tg, cnt, tile_keys, b0);
     }
     rc = launch_scan(ws, sr, stream, "tile3_bin_scan");
     if (rc != DPR_OK) return rc;
     {
         LaunchScope scope("tile3_bin_scatter", stream);
-        tile_bin_kernel<T, N_IN, true><<<gridDim3, 256, 0, stream>>>(pts4, (int)P, rotation, translation, grid, pl.tg, cnt, entries, b0);
+        tile_scatter_kernel<<<gridDim3, 256, 0, stream>>>((int)P, cnt, tile_keys, entries);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;

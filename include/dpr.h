@@ -139,8 +139,8 @@ enum dpr_option {
     DPR_OPT_FORWARD_ACCUM = 5,  /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
     DPR_OPT_POINT_SORT = 6,     /* 0 auto, 1 always sort the points first (pullback: spatially; forward: also by
                                    radius for the one-slab Float32 tile kernel), 2 never                      */
-    DPR_OPT_TILE3D_TMA = 7      /* 3-d tile pullback: 0 cooperative 16-byte tile loads, 1 tensor-map TMA
-                                   (cp.async.bulk.tensor.4d; faults on some driver stacks)      */
+    DPR_OPT_TILE3D_TMA = 7      /* 3-d tile pullback: 0 auto (tensor-map TMA tile loads, cp.async.bulk.tensor.4d, when rows
+                                   are 16-byte multiples), 1 cooperative tile loads only                        */
 };
 int dpr_set_option(int option, int64_t value);
 int64_t dpr_get_option(int option);
@@ -148,7 +148,8 @@ int64_t dpr_get_option(int option);
 int64_t dpr_kernel_launch_count(void);
 /* Per-kernel timing for benchmarks: while enabled, every kernel launch is bracketed with CUDA events on its stream.
  * dpr_profile_enable(on) also clears the records; dpr_profile_get synchronises on record i and returns its name
- * (static string) and duration in milliseconds. */
+ * (static string) and duration in milliseconds.  on = 2 is a checked mode for debugging: every launch is followed by a
+ * stream synchronise and a kernel that faulted is named in dpr_last_error_message() and on stderr. */
 int dpr_profile_enable(int on);
 int dpr_profile_count(void);
 int dpr_profile_get(int i, const char** name, float* ms);

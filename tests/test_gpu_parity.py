@@ -738,7 +738,7 @@ def test_tile3d_paths(dtype, grid, weights):
     d["points"][:, :7] *= 6.0            # a few points far outside the cube (src/raster.jl:62: skipped per corner)
     with forced(forward_algo=3, pullback_algo=7):
         _check(d, grid, dtype, f"tile3d {grid}")
-        assert dpr_b200.last_path(0) == "tile3d_binned" and dpr_b200.last_path(1).startswith("tile3d_binned")
+        assert dpr_b200.last_path(0).startswith("tile3d_binned") and dpr_b200.last_path(1).startswith("tile3d_binned")
 
 
 def test_tile3d_matches_point_parallel_kernels_and_edge_cases():
@@ -760,7 +760,7 @@ def test_tile3d_matches_point_parallel_kernels_and_edge_cases():
     with forced(forward_algo=3, pullback_algo=7):
         out3 = dpr_b200.raster(grid, *args)
         pb3 = dpr_b200.raster_pullback_(ds, *args)
-        assert dpr_b200.last_path(0) == "tile3d_binned"
+        assert dpr_b200.last_path(0).startswith("tile3d_binned")
         e = dpr_b200.empty_f((3, 0), torch.float64, "cuda")
         assert dpr_b200.raster(grid, e, *args[1:5], None).shape == out3.shape     # P = 0 falls back to the fill
     assert rel_l2(to_np(out3), to_np(out1)) < 1e-13
@@ -776,4 +776,4 @@ def test_tile3d_auto_selected_for_dense_volumes():
     grid = (64, 64, 64)
     d = make_inputs(17, 3, 3, 200_000, 16, grid, np.float32, weights=False)
     _check(d, grid, np.float32, "cfg3 scaled")
-    assert dpr_b200.last_path(0) == "tile3d_binned" and dpr_b200.last_path(1).startswith("tile3d_binned")
+    assert dpr_b200.last_path(0).startswith("tile3d_binned") and dpr_b200.last_path(1).startswith("tile3d_binned")
