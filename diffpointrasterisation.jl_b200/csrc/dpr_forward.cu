@@ -634,24 +634,13 @@ static int forward_tile3d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
         while (head < 14 && (double)(1 << head) < 64.0 * per_cell + 64.0) ++head;
         fixed_bits = 32 - head > 22 ? 22 : 32 - head;
     }
-    static int per_sm_cache[2] = {0, 0};                 // resident CTAs per SM (Float32, Float64): a property of the kernel
-    int& per_sm = per_sm_cache[sizeof(T) == 8];
-    if (per_sm == 0) {
-        int n = 0;
-        DPR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, t3::kCtaThreads, smem));
-        per_sm = n > 0 ? n : 1;
-    }
     for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
         const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
         rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
         if (rc != DPR_OK) return rc;
-        const int64_t n_work = nb * pl.tg.n_tiles;
-        int64_t ctas = (int64_t)dev.sm_count * per_sm;
-        if (ctas > n_work) ctas = n_work;
-        uint32_t* counter = reinterpret_cast<uint32_t*>(ws + pl.tile_scan.off_ticket) + t3::kWorkCounter;
         LaunchScope scope("fwd_tile3d", a.stream);
-        kern<<<(unsigned)ctas, t3::kCtaThreads, smem, a.stream>>>(pts4, entries, cnt, a.rotation, a.translation, a.background, a.out_weight,
-                                                              a.out, grid, pl.tg, b0, (int)n_work, counter, pw_stats, a.P, fixed_bits);
+        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, smem, a.stream>>>(pts4, entries, cnt, a.rotation, a.translation, a.background,
+                                                                              a.out_weight, a.out, grid, pl.tg, b0, pw_stats, a.P, fixed_bits);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     set_last_path(DPR_OP_FORWARD, fixed_bits ? "tile3d_binned_fixed" : "tile3d_binned");

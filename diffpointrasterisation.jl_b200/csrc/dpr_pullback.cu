@@ -397,31 +397,21 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
     t3::Pt4<T>* acc4 = reinterpret_cast<t3::Pt4<T>*>(ws + pl.off_acc4);
     const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ws + pl.tile_scan.off_data);
     const uint32_t* entries = reinterpret_cast<const uint32_t*>(ws + pl.off_entries);
-    auto launch = [&](auto kern, size_t smem, int& per_sm, int64_t b0, int64_t nb) -> int {
-        const int rcs = opt_in_smem_once(kern, smem, dev);
+    auto launch = [&](auto kern, int64_t b0, int64_t nb) -> int {
+        const int rcs = opt_in_smem_once(kern, tile_bytes, dev);
         if (rcs != DPR_OK) return rcs;
-        if (per_sm == 0) {                                    // resident CTAs per SM: a property of the kernel
-            int n = 0;
-            DPR_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, t3::kPbThreads, smem));
-            per_sm = n > 0 ? n : 1;
-        }
-        const int64_t n_work = nb * pl.tg.n_tiles;
-        int64_t ctas = (int64_t)dev.sm_count * per_sm;
-        if (ctas > n_work) ctas = n_work;
-        uint32_t* counter = reinterpret_cast<uint32_t*>(ws + pl.tile_scan.off_ticket) + t3::kWorkCounter;
         LaunchScope scope("pullback_tile3d", a.stream);
-        kern<<<(unsigned)ctas, t3::kPbThreads, smem, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation, a.translation, a.out_weight,
-                                                              acc4, a.d_rotation, a.d_translation, a.d_background, a.d_out_weight, grid,
-                                                              pl.tg, b0, (int)n_work, counter);
+        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, tile_bytes, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation,
+                                                                                    a.translation, a.out_weight, acc4, a.d_rotation,
+                                                                                    a.d_translation, a.d_background, a.d_out_weight, grid,
+                                                                                    pl.tg, b0);
         return DPR_OK;
     };
-    static int per_sm_cache[2][2] = {{0, 0}, {0, 0}};
     for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
         const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
         rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
         if (rc != DPR_OK) return rc;
-        rc = use_tma ? launch(t3::pullback_tile3d_kernel<T, N_IN, true>, t3::kStages * tile_bytes, per_sm_cache[1][sizeof(T) == 8], b0, nb)
-                     : launch(t3::pullback_tile3d_kernel<T, N_IN, false>, tile_bytes, per_sm_cache[0][sizeof(T) == 8], b0, nb);
+        rc = use_tma ? launch(t3::pullback_tile3d_kernel<T, N_IN, true>, b0, nb) : launch(t3::pullback_tile3d_kernel<T, N_IN, false>, b0, nb);
         if (rc != DPR_OK) return rc;
     }
     {

@@ -294,134 +294,107 @@ static __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 5. the tile kernels.  Both are PERSISTENT and WARP-SPECIALISED: a CTA has eight consumer warps and one producer warp.
+// 5. the tile kernels: one CTA per (pose, tile) work item, 256 threads, at most ~50 (forward) / 64 (pullback) registers so
+// that five / four CTAs share an SM and the hardware scheduler overlaps their phases (range look-up, entry gathers,
+// accumulation, flush).
 //
-// The producer warp pulls (pose, tile) work items from a global counter kBatch at a time (one atomic per batch, taken two
-// batches ahead: heavy tiles in the core of the cloud and empty ones at the rim balance out dynamically), and each of its
-// lanes prepares one item: it fetches the bounds of the up to 27 sub-lists the tile has to walk - its own 8 plus, for
-// each of its 7 lower neighbours t - d, those whose pattern contains d - and writes a COMPACT table of the non-empty ones
-// (own interior list first) into a two-batch ring in shared memory, published through an mbarrier.  In the pullback it
-// also issues the tensor-map TMA copies of the ds_dout tiles, kStages - 1 items ahead of the consumers.  The consumers
-// never touch global bookkeeping: they wait on the item's mbarrier, process it, release it.
-//   History (profiles/ncu_r02_*_cfg3_summary.txt): one CTA per item spent 23 % of its stall samples on the first constant
-//   load of a fresh CTA and ~40 % of its instructions on per-CTA set-up; a persistent CTA whose warp 0 did the bookkeeping
-//   one item ahead between two block barriers spent 32 % of its samples in those barriers, waiting for the ticket atomic
-//   and the range loads whenever a tile had little work - and most tiles have.
+// What was measured on config 3 before settling here (profiles/ncu_r02_*_cfg3_summary.txt; all on the same B200 pool):
+//   v2  CTA per item, float CAS atomics, div/mod in the flush        fwd 467 us (273 M warp instructions, issue 51 %)
+//   v2b + fixed-point atomics                                          fwd 414 us (324 M, issue 68 %, 39 warps / SM)
+//   v3  persistent CTAs, warp 0 does the bookkeeping between barriers  fwd 421 us, pullback 498 us (barrier stalls 32 %)
+//   v5  warp-specialised persistent CTAs (metadata producer warp, TMA  fwd 535 us, pullback 464 us: 190 M / 150 M
+//       producer warp, mbarrier rings, cross-item look-ahead)          instructions but 72 - 93 registers -> 20 - 27 warps
+//                                                                      per SM, issue 39 %: latency bound; forcing 56 - 64
+//                                                                      registers (spills) made it 675 / 889 us
+// The instruction-lean pieces of v3 - v5 (division-free cell map, compact sub-list table, fixed-point accumulation,
+// factorised trilinear gradient, tensor-map TMA tile loads) are kept; the bookkeeping went back to the hardware.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int kConsumers = kThreads;              // 8 consumer warps
-constexpr int kCtaThreads = kConsumers + 32;      // + the producer warp
-constexpr int kBatch = 16;                        // items per metadata batch (one per producer lane)
 constexpr int kMaxSlots = 27;
-constexpr int kWorkCounter = 8;                   // word of the tile scan region's header used as the global work counter
 
-struct ItemMeta {
-    int w;                         // work item (>= n_work: no more work)
-    int bl, tx, ty, tz;            // pose (local to the pass), tile coordinates
-    int n_slots;                   // non-empty sub-lists
+// the 27 (lower-neighbour offset d, pattern) combinations with pattern containing d; combination 0 is the tile's own
+// pattern-0 list (stencils entirely inside the tile)
+__device__ __constant__ unsigned char kComboD[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 7, 0, 0, 0, 0, 0};
+__device__ __constant__ unsigned char kComboPat[32] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 3, 5, 7, 2, 3, 6, 7, 3, 7, 4, 5, 6, 7, 5, 7, 6, 7, 7, 0, 0, 0, 0, 0};
+
+// compact table of the non-empty sub-lists of one item, built by warp 0
+struct SlotTable {
+    int n_slots;
     uint32_t total;                // entries over all sub-lists
     uint32_t n_interior;           // length of the tile's own pattern-0 list (always slot 0 when non-empty)
     uint32_t base[kMaxSlots];      // sub-list s holds concatenated entries e in [end[s-1], end[s]) at entries[base[s] + e]
     uint32_t end[kMaxSlots];
 };
-
-__device__ __forceinline__ void bar_sync_consumers() { asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory"); }
-
-__device__ __forceinline__ void decode_work(ItemMeta& it, int w, const TileGeom& tg) {
-    it.w = w;
-    it.bl = w / tg.n_tiles;
-    const int t = w - it.bl * tg.n_tiles;
-    const int row = tg.nt[0] * tg.nt[1];
-    it.tz = t / row;
-    const int r = t - it.tz * row;
-    it.ty = r / tg.nt[0];
-    it.tx = r - it.ty * tg.nt[0];
-}
-
-// producer lane: the raw bounds of the 27 sub-lists of one item (loads issued here, consumed in meta_finish)
-struct MetaLoad {
-    uint32_t s[kMaxSlots], e[kMaxSlots];
-};
-__device__ __forceinline__ void meta_issue(MetaLoad& ml, const ItemMeta& it, bool valid, const uint32_t* __restrict__ cnt, const TileGeom& tg) {
-    int c = 0;
-#pragma unroll
-    for (int d = 0; d < 8; ++d) {
-#pragma unroll
-        for (int pat = 0; pat < 8; ++pat) {
-            if ((pat & d) != d) continue;
-            const int nx = it.tx - (d & 1), ny = it.ty - ((d >> 1) & 1), nz = it.tz - ((d >> 2) & 1);
-            uint32_t s = 0, e = 0;
-            if (valid && nx >= 0 && ny >= 0 && nz >= 0) {
-                const uint32_t tile = (uint32_t)((nz * tg.nt[1] + ny) * tg.nt[0] + nx);
-                const uint32_t key = (((uint32_t)it.bl * (uint32_t)tg.n_tiles + tile) << 3) | (uint32_t)pat;
-                e = __ldg(cnt + key);                       // after the scatter pass cnt[key] is the END of list `key`
-                s = key ? __ldg(cnt + key - 1) : 0u;
-            }
-            ml.s[c] = s;
-            ml.e[c] = e;
-            ++c;
-        }
+__device__ __forceinline__ void build_slot_table(SlotTable& tab, const uint32_t* __restrict__ cnt, const TileGeom& tg, int bl,
+                                                 int tx, int ty, int tz) {
+    if (threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    const int d = kComboD[lane], pat = kComboPat[lane];
+    const int nx = tx - (d & 1), ny = ty - ((d >> 1) & 1), nz = tz - ((d >> 2) & 1);
+    uint32_t s = 0, e = 0;
+    if (lane < kMaxSlots && nx >= 0 && ny >= 0 && nz >= 0) {
+        const uint32_t tile = (uint32_t)((nz * tg.nt[1] + ny) * tg.nt[0] + nx);
+        const uint32_t key = (((uint32_t)bl * (uint32_t)tg.n_tiles + tile) << 3) | (uint32_t)pat;
+        e = __ldg(cnt + key);                           // after the scatter pass cnt[key] is the END of list `key`
+        s = key ? __ldg(cnt + key - 1) : 0u;
     }
-}
-__device__ __forceinline__ void meta_finish(ItemMeta& out, const ItemMeta& it, const MetaLoad& ml) {
-    out.w = it.w; out.bl = it.bl; out.tx = it.tx; out.ty = it.ty; out.tz = it.tz;
-    uint32_t run = 0;
-    int n = 0;
-    out.n_interior = ml.e[0] - ml.s[0];                     // combination 0 is (d = 0, pattern = 0)
+    const uint32_t len = e - s;
+    uint32_t incl = len;
 #pragma unroll
-    for (int c = 0; c < kMaxSlots; ++c) {
-        const uint32_t len = ml.e[c] - ml.s[c];
-        if (len) {
-            out.base[n] = ml.s[c] - run;
-            run += len;
-            out.end[n] = run;
-            ++n;
-        }
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
     }
-    out.n_slots = n;
-    out.total = run;
+    const unsigned mask = __ballot_sync(0xffffffffu, len != 0u);
+    if (len) {
+        const int pos = __popc(mask & ((1u << lane) - 1u));
+        tab.base[pos] = s - (incl - len);
+        tab.end[pos] = incl;
+    }
+    if (lane == 0) { tab.n_slots = __popc(mask); tab.n_interior = len; }
+    if (lane == 31) tab.total = incl;
 }
 
-// Walks the compact sub-list table of an item as one sequence: index e of the concatenation -> sorted point index.
+// Walks the compact sub-list table as one sequence: index e of the concatenation -> sorted point index.
 struct EntryCursor {
-    const ItemMeta* m;
+    const SlotTable* t;
     const uint32_t* entries;
     int slot;
     uint32_t bound, base;
-    __device__ __forceinline__ void init(const ItemMeta* meta, const uint32_t* en) {
-        m = meta; entries = en; slot = 0;
-        bound = meta->end[0];
-        base = meta->base[0];
+    __device__ __forceinline__ void init(const SlotTable* tab, const uint32_t* en) {
+        t = tab; entries = en; slot = 0;
+        bound = tab->end[0];
+        base = tab->base[0];
     }
     __device__ __forceinline__ uint32_t fetch(uint32_t e) {
         if (e >= bound) {
-            do { ++slot; bound = m->end[slot]; } while (e >= bound);
-            base = m->base[slot];
+            do { ++slot; bound = t->end[slot]; } while (e >= bound);
+            base = t->base[slot];
         }
         return __ldg(entries + (uint32_t)(base + e));       // 32-bit sum: base may have wrapped below zero
     }
 };
 
-__device__ __forceinline__ long long consumer_sum_i64(long long v, long long* scratch /* [kConsumers / 32] */) {
+__device__ __forceinline__ long long block_sum_i64(long long v, long long* scratch /* [kThreads / 32] */) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    bar_sync_consumers();
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
-    bar_sync_consumers();
+    __syncthreads();
     long long t = 0;
 #pragma unroll
-    for (int i = 0; i < kConsumers / 32; ++i) t += scratch[i];
+    for (int i = 0; i < kThreads / 32; ++i) t += scratch[i];
     return t;
 }
 
-// Thread <-> tile cell mapping of the flush / tile sums: 16-byte piece r (r = 0 .. kPieces-1) of consumer thread tid is
+// Thread <-> tile cell mapping of the flush / tile sums: 16-byte piece r (r = 0 .. kPieces-1) of thread tid is
 // (x4, y, z0 + r * kZStep) with everything but z fixed per thread - no division in the loops.
 template <typename T>
 struct CellMap {
     static constexpr int VEC = 16 / sizeof(T);
-    static constexpr int PX = TX / VEC;                              // pieces per row
-    static constexpr int kPieces = kTileCells / VEC / kConsumers;    // per thread
-    static constexpr int kZStep = kConsumers / (PX * TY);            // z advance per r
-    static_assert(kConsumers % (PX * TY) == 0 && kPieces * kZStep == TZ, "tile / CTA shape mismatch");
+    static constexpr int PX = TX / VEC;                            // pieces per row
+    static constexpr int kPieces = kTileCells / VEC / kThreads;    // per thread
+    static constexpr int kZStep = kThreads / (PX * TY);            // z advance per r
+    static_assert(kThreads % (PX * TY) == 0 && kPieces * kZStep == TZ, "tile / CTA shape mismatch");
     int x4, y, z0;
     __device__ __forceinline__ CellMap() {
         const int tid = threadIdx.x;
@@ -430,94 +403,6 @@ struct CellMap {
         z0 = tid / (PX * TY);
     }
 };
-
-// the metadata ring (two batches), shared by both kernels
-struct MetaRing {
-    ItemMeta items[2 * kBatch];
-    uint64_t full[2], empty[2];     // mbarriers: batch published (count 1) / batch consumed (count = consumer warps)
-};
-__device__ __forceinline__ const ItemMeta& ring_item(const MetaRing& ring, int g) {
-    return ring.items[((g / kBatch) & 1) * kBatch + g % kBatch];
-}
-__device__ __forceinline__ void ring_wait_batch(MetaRing& ring, int batch) {
-    mbar_wait(&ring.full[batch & 1], (uint32_t)((batch >> 1) & 1));
-}
-
-// The metadata producer warp: batch k + 1 is published as soon as the consumers have released batch k - 1, i.e. a whole
-// batch ahead of its first use; the ticket of batch k + 2 and the range loads of batch k + 1 are in flight meanwhile.
-__device__ __forceinline__ void produce_metadata(MetaRing& ring, const uint32_t* __restrict__ cnt, const TileGeom& tg, int n_work,
-                                                 uint32_t* __restrict__ work_counter) {
-    const int lane = threadIdx.x & 31;
-    int base_cur = 0, base_next = 0;
-    if (lane == 0) { base_cur = (int)atomicAdd(work_counter, (uint32_t)kBatch); base_next = (int)atomicAdd(work_counter, (uint32_t)kBatch); }
-    base_cur = __shfl_sync(0xffffffffu, base_cur, 0);
-    base_next = __shfl_sync(0xffffffffu, base_next, 0);
-    ItemMeta it;
-    MetaLoad ml;
-    decode_work(it, base_cur + lane, tg);                    // batch 0
-    meta_issue(ml, it, lane < kBatch && it.w < n_work, cnt, tg);
-    if (lane < kBatch) meta_finish(ring.items[lane], it, ml);
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&ring.full[0]);
-    for (int k = 0;; ++k) {
-        if (base_cur >= n_work) break;                       // batch k ends the work: the consumers stop inside it
-        int base_next2 = 0;
-        if (lane == 0) base_next2 = (int)atomicAdd(work_counter, (uint32_t)kBatch);        // batch k + 2, used after this batch
-        decode_work(it, base_next + lane, tg);
-        meta_issue(ml, it, lane < kBatch && it.w < n_work, cnt, tg);
-        if (k + 1 >= 2) mbar_wait(&ring.empty[(k + 1) & 1], (uint32_t)((((k + 1) >> 1) - 1) & 1));   // batch k - 1 consumed
-        if (lane < kBatch) meta_finish(ring.items[((k + 1) & 1) * kBatch + lane], it, ml);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ring.full[(k + 1) & 1]);
-        base_cur = base_next;
-        base_next = __shfl_sync(0xffffffffu, base_next2, 0);
-    }
-}
-
-// Consumer-side look-ahead across items.  Most tiles hold only a few entries per thread, so the dependent loads
-// (entry -> point) at the start of every item were exposed (profiles/ncu_r02_e_cfg3_summary.txt: a quarter of the stall
-// samples): every consumer thread therefore keeps the index of ITS first entry (e = tid) of item g + 2 and the point of
-// its first entry of item g + 1 in flight while it works on item g.
-constexpr int kLaIdx = 3, kLaPt = 1;
-template <typename T>
-struct Lookahead {
-    uint32_t idx[kLaIdx];      // before item g: first entry of this thread in items g .. g + 3 (0 when it has none)
-    Pt4<T> q[kLaPt];           // points of idx[0], idx[1]
-    __device__ __forceinline__ void init(const MetaRing& ring, int n_work, const uint32_t* __restrict__ entries, const Pt4<T>* __restrict__ pts4);
-    // take item g's first entry; item g + 2's point and item g + 4's index take off
-    __device__ __forceinline__ void rotate(MetaRing& ring, int g, int n_work, const uint32_t* __restrict__ entries,
-                                           const Pt4<T>* __restrict__ pts4, uint32_t& idx_first, Pt4<T>& q_first);
-};
-__device__ __forceinline__ uint32_t first_entry(const ItemMeta& m, int n_work, const uint32_t* __restrict__ entries) {
-    uint32_t idx = 0;
-    if (m.w < n_work && threadIdx.x < m.total) {
-        int s = 0;
-        while (threadIdx.x >= m.end[s]) ++s;
-        idx = __ldg(entries + (uint32_t)(m.base[s] + threadIdx.x));
-    }
-    return idx;
-}
-template <typename T>
-__device__ __forceinline__ void Lookahead<T>::init(const MetaRing& ring, int n_work, const uint32_t* __restrict__ entries,
-                                                    const Pt4<T>* __restrict__ pts4) {
-#pragma unroll
-    for (int k = 0; k < kLaIdx; ++k) idx[k] = first_entry(ring_item(ring, k), n_work, entries);      // kLaIdx <= kBatch: all in batch 0
-#pragma unroll
-    for (int k = 0; k < kLaPt; ++k) q[k] = pts4[idx[k]];
-}
-template <typename T>
-__device__ __forceinline__ void Lookahead<T>::rotate(MetaRing& ring, int g, int n_work, const uint32_t* __restrict__ entries,
-                                                      const Pt4<T>* __restrict__ pts4, uint32_t& idx_first, Pt4<T>& q_first) {
-    idx_first = idx[0];
-    q_first = q[0];
-#pragma unroll
-    for (int k = 0; k + 1 < kLaIdx; ++k) idx[k] = idx[k + 1];
-#pragma unroll
-    for (int k = 0; k + 1 < kLaPt; ++k) q[k] = q[k + 1];
-    q[kLaPt - 1] = pts4[idx[kLaPt - 1]];
-    if ((g + kLaIdx) % kBatch == 0) ring_wait_batch(ring, (g + kLaIdx) / kBatch);       // published a batch ahead: no stall in steady state
-    idx[kLaIdx - 1] = first_entry(ring_item(ring, g + kLaIdx), n_work, entries);
-}
 
 // ---------------------------------------------------------------------------------------------------------
 // 5a. forward: accumulate in shared memory, one store per output cell (src/raster.jl:27,36-66)
@@ -532,8 +417,7 @@ __device__ __forceinline__ void Lookahead<T>::rotate(MetaRing& ring, int g, int 
 // float atomics, as it is for poses / weights that are not eligible (non-positive out_weight, negative or non-finite
 // point weights, dynamic range above 64).
 // The tile rows are padded by one 16-byte piece and the planes by two: spatially sorted entries put the 32 lanes of a warp
-// into a blob a few cells wide, and with a dense 32-float pitch the bank would depend on x only (6 wavefronts per atomic in
-// the first version).  The tile is zero when an item starts: the flush reads each cell once, stores it, writes the zero back.
+// into a blob a few cells wide, and with a dense 32-float pitch the bank would depend on x only (6 wavefronts per atomic).
 // ---------------------------------------------------------------------------------------------------------
 template <typename T>
 struct FwdTile {
@@ -544,263 +428,229 @@ struct FwdTile {
 };
 
 template <typename T, int N_IN>
-__global__ void __launch_bounds__(kCtaThreads, sizeof(T) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
 fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt,
                   const T* __restrict__ rotation, const T* __restrict__ translation, const T* __restrict__ background,
-                  const T* __restrict__ out_weight, T* __restrict__ out, Grid<T, 3> grid, TileGeom tg, int64_t b0, int n_work,
-                  uint32_t* __restrict__ work_counter, const uint32_t* __restrict__ pw_stats, int64_t P, int fixed_bits) {
+                  const T* __restrict__ out_weight, T* __restrict__ out, Grid<T, 3> grid, TileGeom tg, int64_t b0,
+                  const uint32_t* __restrict__ pw_stats, int64_t P, int fixed_bits) {
     using CM = CellMap<T>;
     using FT = FwdTile<T>;
     constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
     T* tile = reinterpret_cast<T*>(smem_raw);
-    __shared__ __align__(16) MetaRing ring;
-    __shared__ long long scratch[kConsumers / 32];
-    const int lane = threadIdx.x & 31;
+    __shared__ SlotTable tab;
+    __shared__ long long scratch[kThreads / 32];
+    const int bl = blockIdx.x / tg.n_tiles;
+    const int t = blockIdx.x - bl * tg.n_tiles;
+    const int row = tg.nt[0] * tg.nt[1];
+    const int tz = t / row, ty = (t - tz * row) / tg.nt[0], tx = t - tz * row - ty * tg.nt[0];
+    const int64_t b = b0 + bl;
+    build_slot_table(tab, cnt, tg, bl, tx, ty, tz);
 
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < 2; ++k) { mbar_init(&ring.full[k], 1); mbar_init(&ring.empty[k], kConsumers / 32); }
-        mbar_fence_init();
-    }
-    for (int i = threadIdx.x; i < FT::SIZE / VEC; i += kCtaThreads) {
-        Pack z;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
-        reinterpret_cast<Pack*>(tile)[i] = z;
-    }
-    __syncthreads();
-
-    if (threadIdx.x >= kConsumers) {
-        produce_metadata(ring, cnt, tg, n_work, work_counter);          // ================= producer warp =================
-        return;
-    }
-
-    // ================= consumer warps =================
     const CM cm;
+    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
+    const T bg = background ? __ldg(background + b) : T(0);
     const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(out) % 16) == 0;
     const int64_t plane = (int64_t)grid.g[0] * grid.g[1];
     T* const my_cells = tile + (cm.z0 * FT::PLANE + cm.y * FT::PITCH + cm.x4);      // + r * kZStep * PLANE
+    T* __restrict__ dst0 = out + b * grid.cells + ((int64_t)(oz + cm.z0) * grid.g[1] + (oy + cm.y)) * grid.g[0] + (ox + cm.x4);
+    const bool col_ok = ox + cm.x4 < grid.g[0] && oy + cm.y < grid.g[1];
+    const bool full_vec = vec_ok && ox + cm.x4 + VEC <= grid.g[0];
+    const int z_lim = grid.g[2] - oz - cm.z0;            // piece r is inside the volume iff r * kZStep < z_lim
+    float inv_q = 0.f;
 
-    // fixed-point statistics of the point weights (uniform, once)
-    bool pw_ok = true;
-    int em = 0;
+    // stores value(cell) + bg for this thread's cells inside the volume.
+    // MODE 0: background only (no shared-memory access); 1: float cells; 2: fixed-point cells; 3: fixed point + cell sum,
+    // and the cells are zeroed for a possible second pass
+    auto flush = [&](auto mode_tag) -> long long {
+        constexpr int MODE = decltype(mode_tag)::value;
+        unsigned long long cells = 0;
+        T* dst = dst0;
+#pragma unroll
+        for (int r = 0; r < CM::kPieces; ++r, dst += CM::kZStep * plane) {
+            Pack pk;
+            if constexpr (MODE == 0) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) pk.v[k] = bg;
+            } else {
+                Pack* cell = reinterpret_cast<Pack*>(my_cells + r * CM::kZStep * FT::PLANE);
+                pk = *cell;
+                if constexpr (MODE >= 2 && sizeof(T) == 4) {
+                    if constexpr (MODE == 3) {
+                        Pack z;
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
+                        *cell = z;
+                    }
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) {
+                        const uint32_t u = __float_as_uint(pk.v[k]);
+                        if constexpr (MODE == 3) cells += u;
+                        pk.v[k] = fmaf((float)u, inv_q, bg);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) pk.v[k] += bg;
+                }
+            }
+            if (!col_ok || r * CM::kZStep >= z_lim) continue;
+            if (full_vec) {
+                __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(&pk));
+            } else {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) if (ox + cm.x4 + k < grid.g[0]) dst[k] = pk.v[k];
+            }
+        }
+        return (long long)cells;
+    };
+    auto zero_tile = [&]() {
+#pragma unroll
+        for (int r = 0; r < CM::kPieces; ++r) {
+            Pack z;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
+            *reinterpret_cast<Pack*>(my_cells + r * CM::kZStep * FT::PLANE) = z;
+        }
+    };
+    zero_tile();         // (also the padding stays untouched: it is never read)
+    __syncthreads();
+    const uint32_t total = tab.total;
+    if (total == 0) {            // nothing lands here: the tile is the background (src/raster.jl:27)
+        flush(std::integral_constant<int, 0>{});
+        return;
+    }
+    Pose<T, N_IN, 3> pose;
+    load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b);
+
+    // ---- fixed-point eligibility and scale (uniform over the CTA) ---------------------------------------------
+    bool fixed = false;
+    float wq_den = 0.f, pw_scale = 1.f;
     if constexpr (sizeof(T) == 4) {
+        bool ok = pose.ow > 0.f && fixed_bits > 0;
+        int em = 0;
         if (pw_stats) {
             const float wmax = __uint_as_float(__ldg(pw_stats + kStatMaxBits));
             const float wmean = __uint_as_float(__ldg(pw_stats + kStatSum)) / (float)P;
-            pw_ok = __ldg(pw_stats + kStatBad) == 0u && wmax > 0.f && wmax < 3e38f && wmax <= 64.f * wmean;
-            if (pw_ok) frexpf(wmax, &em);
+            ok = ok && __ldg(pw_stats + kStatBad) == 0u && wmax > 0.f && wmax < 3e38f && wmax <= 64.f * wmean;
+            if (ok) frexpf(wmax, &em);
+        }
+        const float A = ldexpf((float)pose.ow, em);
+        ok = ok && A > 1e-30f && A < 1e30f;
+        if (ok) {
+            int e;
+            frexpf(A, &e);                                        // A < 2^e
+            const float Q = rintf(ldexpf(A, fixed_bits - e));     // 2^(F-1) <= Q <= 2^F <= 2^22
+            wq_den = __int_as_float((int)Q);
+            inv_q = A / Q;
+            pw_scale = ldexpf(1.f, -em);
+            fixed = true;
         }
     }
-    const float pw_scale = ldexpf(1.f, -em);
 
-    int cur_bl = -1;
-    Pose<T, N_IN, 3> pose;
-    T bg = T(0);
-    bool fixed_pose = false;
-    float wq_den = 0.f, inv_q = 0.f;
-
-    ring_wait_batch(ring, 0);
-    Lookahead<T> la;
-    la.init(ring, n_work, entries, pts4);
-    for (int g = 0;; ++g) {
-        const int batch = g / kBatch, j = g % kBatch;
-        const ItemMeta& m = ring_item(ring, g);
-        if (m.w >= n_work) break;
-        uint32_t idx_first;
-        Pt4<T> q_first;
-        la.rotate(ring, g, n_work, entries, pts4, idx_first, q_first);
-        if (m.bl != cur_bl) {          // pose parameters and fixed-point scale (uniform over the CTA)
-            cur_bl = m.bl;
-            const int64_t b = b0 + m.bl;
-            load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b);
-            bg = background ? __ldg(background + b) : T(0);
-            fixed_pose = false;
-            if constexpr (sizeof(T) == 4) {
-                bool ok = pw_ok && pose.ow > 0.f && fixed_bits > 0;
-                const float A = ldexpf((float)pose.ow, em);
-                ok = ok && A > 1e-30f && A < 1e30f;
-                if (ok) {
-                    int e;
-                    frexpf(A, &e);                                        // A < 2^e
-                    const float Q = rintf(ldexpf(A, fixed_bits - e));     // 2^(F-1) <= Q <= 2^F <= 2^22
-                    wq_den = __int_as_float((int)Q);
-                    inv_q = A / Q;
-                    fixed_pose = true;
-                }
+    long long mass = 0;
+    const uint32_t n_int = tab.n_interior;
+    // one pass over the item's entries.  FIXED: accumulation mode.  Entries below n_int are the tile's own pattern-0
+    // list, whose stencils lie inside the tile (only the volume's faces can still clip them: the checked path)
+    auto accumulate = [&](auto fixed_tag) {
+        constexpr bool FIXED = decltype(fixed_tag)::value;
+        uint32_t e = threadIdx.x;
+        if (e >= total) return;
+        EntryCursor cur;
+        cur.init(&tab, entries);
+        const uint32_t idx0 = cur.fetch(e);
+        uint32_t idx_n = e + kThreads < total ? cur.fetch(e + kThreads) : 0u;
+        Pt4<T> qn = pts4[idx0];
+        const uint32_t tile_s = smem_u32(tile);
+        for (; e < total; e += kThreads) {
+            const Pt4<T> q = qn;
+            if (e + kThreads < total) qn = pts4[idx_n];
+            if (e + 2 * kThreads < total) idx_n = cur.fetch(e + 2 * kThreads);
+            T x[N_IN];
+            load_xyz<T, N_IN>(x, q);
+            int i0[3];
+            T dl[3], du[3];
+            if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;      // cannot happen: binned with the same arithmetic
+#pragma unroll
+            for (int k = 0; k < 3; ++k) du[k] = T(1) - dl[k];
+            const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
+            // corner values in bit order (x = bit 0): w_c * out_weight * point_weight (src/raster.jl:51,63,104-106),
+            // or its fixed-point image
+            T v[8];
+            if constexpr (FIXED) {
+                const float wq = wq_den * ((float)q.w * pw_scale);
+                const float az[2] = {(float)du[2] * wq, (float)dl[2] * wq};
+                const float byz[4] = {(float)du[1] * az[0], (float)dl[1] * az[0], (float)du[1] * az[1], (float)dl[1] * az[1]};
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = T(((c & 1) ? (float)dl[0] : (float)du[0]) * byz[c >> 1]);
+            } else {
+                const T weight = pose.ow * q.w;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) v[c] = corner_weight<T, 3>(c, dl, du) * weight;
             }
-        }
-        const uint32_t total = m.total;
-        const int ox = m.tx * TX, oy = m.ty * TY, oz = m.tz * TZ;
-        T* __restrict__ dst0 = out + (b0 + m.bl) * grid.cells + ((int64_t)(oz + cm.z0) * grid.g[1] + (oy + cm.y)) * grid.g[0] + (ox + cm.x4);
-        const bool col_ok = ox + cm.x4 < grid.g[0] && oy + cm.y < grid.g[1];
-        const bool full_vec = vec_ok && ox + cm.x4 + VEC <= grid.g[0];
-        const int z_lim = grid.g[2] - oz - cm.z0;            // piece r is inside the volume iff r * kZStep < z_lim
-
-        // stores value(cell) + bg for this thread's cells inside the volume and writes the zero back.
-        // MODE 0: background only (no shared-memory access); 1: float cells; 2: fixed-point cells; 3: fixed point + cell sum
-        auto flush = [&](auto mode_tag) -> long long {
-            constexpr int MODE = decltype(mode_tag)::value;
-            unsigned long long cells = 0;
-            T* dst = dst0;
-#pragma unroll
-            for (int r = 0; r < CM::kPieces; ++r, dst += CM::kZStep * plane) {
-                Pack pk;
-                if constexpr (MODE == 0) {
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) pk.v[k] = bg;
+            uint32_t msum = 0;
+            auto add = [&](int o, T val) {
+                if constexpr (FIXED) {
+                    const uint32_t qv = __float_as_uint((float)val);
+                    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "r"(qv) : "memory");
+                    msum += qv;
                 } else {
-                    Pack* cell = reinterpret_cast<Pack*>(my_cells + r * CM::kZStep * FT::PLANE);
-                    pk = *cell;
-                    Pack z;
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
-                    *cell = z;
-                    if constexpr (MODE >= 2 && sizeof(T) == 4) {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) {
-                            const uint32_t u = __float_as_uint(pk.v[k]);
-                            if constexpr (MODE == 3) cells += u;
-                            pk.v[k] = fmaf((float)u, inv_q, bg);
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) pk.v[k] += bg;
-                    }
-                }
-                if (!col_ok || r * CM::kZStep >= z_lim) continue;
-                if (full_vec) {
-                    __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(&pk));
-                } else {
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) if (ox + cm.x4 + k < grid.g[0]) dst[k] = pk.v[k];
-                }
-            }
-            return (long long)cells;
-        };
-
-        if (total == 0) {            // nothing lands here: the tile is the background (src/raster.jl:27)
-            flush(std::integral_constant<int, 0>{});
-        } else {
-            long long mass = 0;
-            // one pass over the item's entries.  FIXED: accumulation mode.  Entries below n_int are the tile's own pattern-0
-            // list, whose stencils lie inside the tile (only the volume's faces can still clip them: the checked path)
-            const uint32_t n_int = m.n_interior;
-            auto accumulate = [&](auto fixed_tag) {
-                constexpr bool FIXED = decltype(fixed_tag)::value;
-                uint32_t e = threadIdx.x;
-                if (e >= total) return;
-                EntryCursor cur;
-                cur.init(&m, entries);
-                // software pipeline over this thread's entries: index three ahead, point two ahead
-                uint32_t i1 = e + kConsumers < total ? cur.fetch(e + kConsumers) : 0u;
-                uint32_t i2 = e + 2 * kConsumers < total ? cur.fetch(e + 2 * kConsumers) : 0u;
-                Pt4<T> p0 = q_first, p1 = pts4[i1];
-                const uint32_t tile_s = smem_u32(tile);
-                for (; e < total; e += kConsumers) {
-                    const Pt4<T> q = p0;
-                    p0 = p1;
-                    i1 = i2;
-                    if (e + 2 * kConsumers < total) p1 = pts4[i1];
-                    if (e + 3 * kConsumers < total) i2 = cur.fetch(e + 3 * kConsumers);
-                    T x[N_IN];
-                    load_xyz<T, N_IN>(x, q);
-                    int i0[3];
-                    T dl[3], du[3];
-                    if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;      // cannot happen: binned with the same arithmetic
-#pragma unroll
-                    for (int k = 0; k < 3; ++k) du[k] = T(1) - dl[k];
-                    const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
-                    // corner values in bit order (x = bit 0): w_c * out_weight * point_weight (src/raster.jl:51,63,104-106),
-                    // or its fixed-point image
-                    T v[8];
-                    if constexpr (FIXED) {
-                        const float wq = wq_den * ((float)q.w * pw_scale);
-                        const float az[2] = {(float)du[2] * wq, (float)dl[2] * wq};
-                        const float byz[4] = {(float)du[1] * az[0], (float)dl[1] * az[0], (float)du[1] * az[1], (float)dl[1] * az[1]};
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) v[c] = T(((c & 1) ? (float)dl[0] : (float)du[0]) * byz[c >> 1]);
-                    } else {
-                        const T weight = pose.ow * q.w;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) v[c] = corner_weight<T, 3>(c, dl, du) * weight;
-                    }
-                    uint32_t msum = 0;
-                    auto add = [&](int o, T val) {
-                        if constexpr (FIXED) {
-                            const uint32_t qv = __float_as_uint((float)val);
-                            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tile_s + (uint32_t)o * 4u), "r"(qv) : "memory");
-                            msum += qv;
-                        } else {
-                            atomicAdd(tile + o, val);
-                        }
-                    };
-                    const bool inside = e < n_int && (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) &&
-                                        (unsigned)lz < (unsigned)(TZ - 1) && i0[0] + 1 < grid.g[0] && i0[1] + 1 < grid.g[1] && i0[2] + 1 < grid.g[2];
-                    if (inside) {
-                        const int off = lz * FT::PLANE + ly * FT::PITCH + lx;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) add(off + (c & 1) + ((c >> 1) & 1) * FT::PITCH + ((c >> 2) & 1) * FT::PLANE, v[c]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
-                            // inside this item's tile and inside the grid (per-corner bounds rule, src/raster.jl:62)
-                            const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ &&
-                                            ox + cx < grid.g[0] && oy + cy < grid.g[1] && oz + cz < grid.g[2];
-                            if (in) add(cz * FT::PLANE + cy * FT::PITCH + cx, v[c]);
-                        }
-                    }
-                    mass += msum;       // 8 values below 2^22 each: no 32-bit overflow inside one entry
+                    atomicAdd(tile + o, val);
                 }
             };
-            bool done = false;
-            if constexpr (sizeof(T) == 4) {
-                if (fixed_pose) {
-                    accumulate(std::true_type{});
-                    bar_sync_consumers();
-                    // a cell receives at most `total` contributions of at most 2^F: light tiles cannot wrap
-                    const bool can_wrap = ((unsigned long long)total << fixed_bits) >= (1ull << 32);
-                    done = true;
-                    if (!can_wrap) {
-                        flush(std::integral_constant<int, 2>{});
-                    } else {
-                        const long long cells = flush(std::integral_constant<int, 3>{});          // optimistic
-                        if (consumer_sum_i64(cells - mass, scratch) != 0) done = false;    // a wrapped cell: sums differ, exactly
-                    }
-                    bar_sync_consumers();                   // the tile is zero again
+            const bool inside = e < n_int && (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) &&
+                                (unsigned)lz < (unsigned)(TZ - 1) && i0[0] + 1 < grid.g[0] && i0[1] + 1 < grid.g[1] && i0[2] + 1 < grid.g[2];
+            if (inside) {
+                const int off = lz * FT::PLANE + ly * FT::PITCH + lx;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) add(off + (c & 1) + ((c >> 1) & 1) * FT::PITCH + ((c >> 2) & 1) * FT::PLANE, v[c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
+                    // inside this item's tile and inside the grid (per-corner bounds rule, src/raster.jl:62)
+                    const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ &&
+                                    ox + cx < grid.g[0] && oy + cy < grid.g[1] && oz + cz < grid.g[2];
+                    if (in) add(cz * FT::PLANE + cy * FT::PITCH + cx, v[c]);
                 }
             }
-            if (!done) {
-                accumulate(std::false_type{});
-                bar_sync_consumers();
-                flush(std::integral_constant<int, 1>{});
-                bar_sync_consumers();
-            }
+            mass += msum;       // 8 values below 2^22 each: no 32-bit overflow inside one entry
         }
-        if (j == kBatch - 1) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ring.empty[batch & 1]);
+    };
+    if constexpr (sizeof(T) == 4) {
+        if (fixed) {
+            accumulate(std::true_type{});
+            __syncthreads();
+            // a cell receives at most `total` contributions of at most 2^F: light tiles cannot wrap
+            const bool can_wrap = ((unsigned long long)total << fixed_bits) >= (1ull << 32);
+            if (!can_wrap) {
+                flush(std::integral_constant<int, 2>{});
+                return;
+            }
+            const long long cells = flush(std::integral_constant<int, 3>{});          // optimistic; zeroes the tile
+            if (block_sum_i64(cells - mass, scratch) == 0) return;      // else a wrapped cell: the sums differ, exactly
+            __syncthreads();
         }
     }
+    accumulate(std::false_type{});
+    __syncthreads();
+    flush(std::integral_constant<int, 1>{});
 }
 
 // ---------------------------------------------------------------------------------------------------------
 // 5b. pullback (src/raster_pullback.jl:2-82 per pose; ext/DiffPointRasterisationCUDAExt.jl:19-210 is what it replaces)
 //
-// USE_TMA: the producer also fetches the ds_dout tile of every item with ONE 4-d tensor-map TMA copy
-// (cp.async.bulk.tensor, SASS UTMALDG; cells outside the volume arrive as zeros) into a kStages-deep shared-memory ring,
-// kStages - 1 items ahead of the consumers, signalled per stage on a full / empty mbarrier pair.
+// USE_TMA: thread 0 fetches the item's ds_dout tile with ONE 4-d tensor-map TMA copy (cp.async.bulk.tensor, SASS UTMALDG;
+// cells outside the volume arrive as zeros) as the very first thing the CTA does; the range look-up and the first entry /
+// point gathers overlap with it.
 //   (Round 1 had declared tensor-map TMA unusable on this pool - "illegal instruction".  The fault is a constraint, not a
 //    defect: the box must START on a 16-byte boundary in the innermost dimension (c0 * sizeof(T) % 16 == 0), and both
 //    round-1 probes used c0 = -10.  tools/probe_tma_tensor3.cu, profiles/tma_probe_r02.log.  Tile origins are multiples
 //    of TX = 32 cells here.)
-// !USE_TMA (rows that are not 16-byte multiples): the consumers load the tile cooperatively, synchronously.
-// Work items of one CTA increase, so the pose only moves forward: the 3 N_in + 4 per-pose sums and the d_background
-// partial (src/raster_pullback.jl:78: summed from the staged tile, zero outside the volume) stay in registers across items
-// and are block-reduced only when the pose changes.  The sample and its three derivatives come from the factorised
-// trilinear form (25 flops instead of ~150 for the corner-by-corner sums).
+// !USE_TMA (rows that are not 16-byte multiples): the CTA loads the tile cooperatively.
+// d_background (src/raster_pullback.jl:78) is summed from the staged tile (zero outside the volume): ds_dout is read once.
+// The sample and its three derivatives come from the factorised trilinear form (25 flops instead of ~150 for the
+// corner-by-corner sums).
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void tma_load_tile4d(void* dst, const CUtensorMap* map, int c0, int c1, int c2, int c3, uint64_t* bar) {
     asm volatile(
@@ -819,244 +669,202 @@ __device__ __forceinline__ void red_add4(Pt4<double>* addr, double a, double b, 
     atomicAdd(&addr->w, d);
 }
 
-constexpr int kStages = 2;
-
-constexpr int kPbThreads = kConsumers + 64;       // consumers + metadata producer warp + tile (TMA) producer warp
-
 template <typename T, int N_IN, bool USE_TMA>
-__global__ void __launch_bounds__(kPbThreads, sizeof(T) == 4 ? 3 : 1)
+__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
 pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restrict__ ds_dout, const Pt4<T>* __restrict__ pts4,
                        const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt, const T* __restrict__ rotation,
                        const T* __restrict__ translation, const T* __restrict__ out_weight, Pt4<T>* __restrict__ acc4,
                        T* __restrict__ d_rotation, T* __restrict__ d_translation, T* __restrict__ d_background,
-                       T* __restrict__ d_out_weight, Grid<T, 3> grid, TileGeom tg, int64_t b0, int n_work,
-                       uint32_t* __restrict__ work_counter) {
+                       T* __restrict__ d_out_weight, Grid<T, 3> grid, TileGeom tg, int64_t b0) {
     constexpr int NR = 3 * N_IN, NV = NR + 3 + 1;     // d_rotation (col-major 3 x N_IN), d_translation, d_out_weight
     using CM = CellMap<T>;
     constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* const stages = reinterpret_cast<T*>(smem_raw);     // kStages (TMA) or 1 (cooperative loads) tiles of kTileCells
-    __shared__ __align__(16) MetaRing ring;
-    __shared__ __align__(8) uint64_t tile_full[kStages], tile_empty[kStages];
-    __shared__ T red[kConsumers / 32][NV + 1];
+    T* tile = reinterpret_cast<T*>(smem_raw);
+    __shared__ SlotTable tab;
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ T red[kThreads / 32][NV + 1];
+    const int bl = blockIdx.x / tg.n_tiles;
+    const int t = blockIdx.x - bl * tg.n_tiles;
+    const int row = tg.nt[0] * tg.nt[1];
+    const int tz = t / row, ty = (t - tz * row) / tg.nt[0], tx = t - tz * row - ty * tg.nt[0];
+    const int64_t b = b0 + bl;
+    const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const CM cm;
 
-    if (threadIdx.x == 0) {
-        for (int k = 0; k < 2; ++k) { mbar_init(&ring.full[k], 1); mbar_init(&ring.empty[k], kConsumers / 32); }
-        for (int k = 0; k < kStages; ++k) { mbar_init(&tile_full[k], 1); mbar_init(&tile_empty[k], kConsumers / 32); }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if (threadIdx.x >= kConsumers + 32) {
-        // ================= tile producer warp: one tensor-map TMA copy per item, kStages - 1 items ahead =================
-        if (USE_TMA) {
-            for (int g = 0;; ++g) {
-                if (g % kBatch == 0) ring_wait_batch(ring, g / kBatch);
-                const ItemMeta& m = ring_item(ring, g);
-                if (m.w >= n_work) break;
-                const int stage = g % kStages;
-                if (g >= kStages) mbar_wait(&tile_empty[stage], (uint32_t)(((g / kStages) - 1) & 1));     // consumers released it
-                if (lane == 0) {
-                    mbar_arrive_expect_tx(&tile_full[stage], (uint32_t)(kTileCells * sizeof(T)));
-                    tma_load_tile4d(stages + (size_t)stage * kTileCells, &map, m.tx * TX, m.ty * TY, m.tz * TZ, (int)(b0 + m.bl), &tile_full[stage]);
+    if (USE_TMA) {
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(&bar, (uint32_t)(kTileCells * sizeof(T)));
+            tma_load_tile4d(tile, &map, ox, oy, oz, (int)b, &bar);          // cells outside the volume arrive as zeros
+        }
+    } else {
+        const T* __restrict__ img = ds_dout + b * grid.cells;
+        const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) % 16) == 0;
+#pragma unroll
+        for (int r = 0; r < CM::kPieces; ++r) {
+            const int gx = ox + cm.x4, gy = oy + cm.y, gz = oz + cm.z0 + r * CM::kZStep;
+            Pack pk;
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) pk.v[k] = T(0);
+            if (gx < grid.g[0] && gy < grid.g[1] && gz < grid.g[2]) {
+                const T* src = img + ((int64_t)gz * grid.g[1] + gy) * grid.g[0] + gx;
+                if (vec_ok && gx + VEC <= grid.g[0]) {
+                    const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
+                    pk = *reinterpret_cast<const Pack*>(&q);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) if (gx + k < grid.g[0]) pk.v[k] = __ldg(src + k);
                 }
             }
+            reinterpret_cast<Pack*>(tile)[r * kThreads + threadIdx.x] = pk;
+        }
+    }
+    build_slot_table(tab, cnt, tg, bl, tx, ty, tz);
+    __syncthreads();                       // table (and the mbarrier init / the cooperative tile load) visible
+    const uint32_t total = tab.total;
+    if (total == 0 && !d_background) {
+        if (USE_TMA) mbar_wait(&bar, 0);   // never leave a copy in flight into shared memory that the next CTA will own
+        return;
+    }
+
+    // the first entry / point of this thread take off before the tile is waited for
+    EntryCursor cur;
+    uint32_t e = threadIdx.x;
+    uint32_t idx = 0, idx_n = 0;
+    Pt4<T> qn;
+    qn.x = qn.y = qn.z = qn.w = T(0);
+    if (e < total) {
+        cur.init(&tab, entries);
+        idx = cur.fetch(e);
+        if (e + kThreads < total) idx_n = cur.fetch(e + kThreads);
+        qn = pts4[idx];
+    }
+    if (USE_TMA) mbar_wait(&bar, 0);
+
+    T bg_part = T(0);
+    if (d_background) {                    // src/raster_pullback.jl:78 - from the staged tile (zero outside the volume)
+#pragma unroll
+        for (int r = 0; r < CM::kPieces; ++r) {
+            const Pack pk = reinterpret_cast<const Pack*>(tile)[r * kThreads + threadIdx.x];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) bg_part += pk.v[k];
+        }
+    }
+    if (total == 0) {                      // only the tile sum
+        bg_part = warp_sum(bg_part);
+        if (lane == 0) red[warp][0] = bg_part;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            T r = T(0);
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) r += red[w][0];
+            red_add(d_background + b, r);
         }
         return;
     }
-    if (threadIdx.x >= kConsumers) {
-        produce_metadata(ring, cnt, tg, n_work, work_counter);          // ================= metadata producer warp =================
-        return;
-    }
-
-    // ================= consumer warps =================
-    const CM cm;
     T acc[NV];
 #pragma unroll
     for (int v = 0; v < NV; ++v) acc[v] = T(0);
-    T bg_part = T(0);
-    int cur_bl = -1;
     Pose<T, N_IN, 3> pose;
-    // reduce the per-pose sums of pose b0 + cur_bl over the consumers and add them to the outputs (all consumers call it)
-    auto flush_pose = [&]() {
+    load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b);
+    const uint32_t n_int = tab.n_interior;
+    for (; e < total; e += kThreads) {
+        const Pt4<T> q = qn;
+        const uint32_t idx_c = idx;
+        idx = idx_n;
+        if (e + kThreads < total) qn = pts4[idx];
+        if (e + 2 * kThreads < total) idx_n = cur.fetch(e + 2 * kThreads);
+        T x[N_IN];
+        load_xyz<T, N_IN>(x, q);
+        int i0[3];
+        T dl[3];
+        if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;
+        const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
+        // corner values in bit order (x = bit 0).  Corners of other tiles are that tile's item's job (everything is
+        // linear in G); corners outside the volume read the zero fill = skipped (src/raster_pullback.jl:51)
+        T G[8];
+        const bool inside = e < n_int && (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) && (unsigned)lz < (unsigned)(TZ - 1);
+        if (inside) {
+            const int off = (lz * TY + ly) * TX + lx;
 #pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = warp_sum(acc[v]);
-        bg_part = warp_sum(bg_part);
-        bar_sync_consumers();
-        if (lane == 0) {
-#pragma unroll
-            for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
-            red[warp][NV] = bg_part;
-        }
-        bar_sync_consumers();
-        if (threadIdx.x <= NV) {
-            const int v = threadIdx.x;
-            const int64_t b = b0 + cur_bl;
-            T r = T(0);
-#pragma unroll
-            for (int w = 0; w < kConsumers / 32; ++w) r += red[w][v];
-            if (v == NV) { if (d_background) red_add(d_background + b, r); }
-            else if (r != T(0)) {
-                if (v < NR) red_add(d_rotation + b * NR + v, r);
-                else if (v < NR + 3) red_add(d_translation + b * 3 + (v - NR), r);
-                else if (d_out_weight) red_add(d_out_weight + b, r);
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < NV; ++v) acc[v] = T(0);
-        bg_part = T(0);
-    };
-
-    ring_wait_batch(ring, 0);
-    Lookahead<T> la;
-    la.init(ring, n_work, entries, pts4);
-    for (int g = 0;; ++g) {
-        const int batch = g / kBatch, j = g % kBatch;
-        const ItemMeta& m = ring_item(ring, g);
-        if (m.w >= n_work) break;
-        uint32_t idx_first;
-        Pt4<T> q_first;
-        la.rotate(ring, g, n_work, entries, pts4, idx_first, q_first);
-        const int stage = USE_TMA ? g % kStages : 0;
-        if (m.bl != cur_bl) {
-            if (cur_bl >= 0) flush_pose();
-            cur_bl = m.bl;
-            load_pose<T, N_IN, 3>(pose, rotation, translation, out_weight, b0 + m.bl);
-        }
-        const int ox = m.tx * TX, oy = m.ty * TY, oz = m.tz * TZ;
-        T* __restrict__ tile = stages + (size_t)stage * kTileCells;
-        if (USE_TMA) {
-            mbar_wait(&tile_full[stage], (uint32_t)((g / kStages) & 1));      // the tile has landed
+            for (int c = 0; c < 8; ++c) G[c] = tile[off + (c & 1) + ((c >> 1) & 1) * TX + ((c >> 2) & 1) * TX * TY];
         } else {
-            // cooperative synchronous load (any row length / alignment); zero outside the volume
-            bar_sync_consumers();                                             // everyone is done with the previous tile
-            const T* __restrict__ img = ds_dout + (b0 + m.bl) * grid.cells;
-            const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) % 16) == 0;
 #pragma unroll
-            for (int r = 0; r < CM::kPieces; ++r) {
-                const int gx = ox + cm.x4, gy = oy + cm.y, gz = oz + cm.z0 + r * CM::kZStep;
-                Pack pk;
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) pk.v[k] = T(0);
-                if (gx < grid.g[0] && gy < grid.g[1] && gz < grid.g[2]) {
-                    const T* src = img + ((int64_t)gz * grid.g[1] + gy) * grid.g[0] + gx;
-                    if (vec_ok && gx + VEC <= grid.g[0]) {
-                        const float4 q = __ldcs(reinterpret_cast<const float4*>(src));
-                        pk = *reinterpret_cast<const Pack*>(&q);
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < VEC; ++k) if (gx + k < grid.g[0]) pk.v[k] = __ldg(src + k);
-                    }
-                }
-                reinterpret_cast<Pack*>(tile)[r * kConsumers + threadIdx.x] = pk;
-            }
-            bar_sync_consumers();
-        }
-        if (d_background) {                 // src/raster_pullback.jl:78 - from the staged tile (zero outside the volume)
-#pragma unroll
-            for (int r = 0; r < CM::kPieces; ++r) {
-                const Pack pk = reinterpret_cast<const Pack*>(tile)[r * kConsumers + threadIdx.x];
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) bg_part += pk.v[k];
+            for (int c = 0; c < 8; ++c) {
+                const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
+                const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ;
+                G[c] = in ? tile[(cz * TY + cy) * TX + cx] : T(0);
             }
         }
-        const uint32_t total = m.total;
-        // one pass over the item's entries; those below n_interior are the tile's own pattern-0 list (all eight corners on chip)
-        if (threadIdx.x < total) {
-            const uint32_t n_int = m.n_interior;
-            uint32_t e = threadIdx.x;
-            EntryCursor cur;
-            cur.init(&m, entries);
-            // software pipeline over this thread's entries: index three ahead, point two ahead
-            uint32_t i0 = idx_first;
-            uint32_t i1 = e + kConsumers < total ? cur.fetch(e + kConsumers) : 0u;
-            uint32_t i2 = e + 2 * kConsumers < total ? cur.fetch(e + 2 * kConsumers) : 0u;
-            uint32_t ip = i1;                                   // index of the point in p1
-            Pt4<T> p0 = q_first, p1 = pts4[i1];
-            for (; e < total; e += kConsumers) {
-                const Pt4<T> q = p0;
-                const uint32_t idx = i0;
-                p0 = p1;
-                i0 = ip;
-                i1 = i2;
-                ip = i1;
-                if (e + 2 * kConsumers < total) p1 = pts4[i1];
-                if (e + 3 * kConsumers < total) i2 = cur.fetch(e + 3 * kConsumers);
-                T x[N_IN];
-                load_xyz<T, N_IN>(x, q);
-                int i0[3];
-                T dl[3];
-                if (!stencil<T, N_IN, 3>(x, pose, grid, i0, dl)) continue;
-                const int lx = i0[0] - ox, ly = i0[1] - oy, lz = i0[2] - oz;
-                // corner values in bit order (x = bit 0).  Corners of other tiles are that tile's item's job (everything is
-                // linear in G); corners outside the volume read the zero fill = skipped (src/raster_pullback.jl:51)
-                T G[8];
-                const bool inside = e < n_int && (unsigned)lx < (unsigned)(TX - 1) && (unsigned)ly < (unsigned)(TY - 1) && (unsigned)lz < (unsigned)(TZ - 1);
-                if (inside) {
-                    const int off = (lz * TY + ly) * TX + lx;
+        // s = sum_c W_c G_c (src/raster_pullback.jl:55-58) and gk[n] = d s / d dl_n (:60-65, :150-160), factorised:
+        // lerp / difference along x, then y, then z
+        T ax[4], dx[4];
 #pragma unroll
-                    for (int c = 0; c < 8; ++c) G[c] = tile[off + (c & 1) + ((c >> 1) & 1) * TX + ((c >> 2) & 1) * TX * TY];
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int cx = lx + (c & 1), cy = ly + ((c >> 1) & 1), cz = lz + ((c >> 2) & 1);
-                        const bool in = (unsigned)cx < (unsigned)TX && (unsigned)cy < (unsigned)TY && (unsigned)cz < (unsigned)TZ;
-                        G[c] = in ? tile[(cz * TY + cy) * TX + cx] : T(0);
-                    }
-                }
-                // s = sum_c W_c G_c (src/raster_pullback.jl:55-58) and gk[n] = d s / d dl_n (:60-65, :150-160), factorised:
-                // lerp / difference along x, then y, then z
-                T ax[4], dx[4];
-#pragma unroll
-                for (int yz = 0; yz < 4; ++yz) {
-                    dx[yz] = G[2 * yz + 1] - G[2 * yz];
-                    ax[yz] = fma(dl[0], dx[yz], G[2 * yz]);
-                }
-                T by[2], dy[2], ex[2];
-#pragma unroll
-                for (int z = 0; z < 2; ++z) {
-                    dy[z] = ax[2 * z + 1] - ax[2 * z];
-                    by[z] = fma(dl[1], dy[z], ax[2 * z]);
-                    ex[z] = fma(dl[1], dx[2 * z + 1] - dx[2 * z], dx[2 * z]);
-                }
-                T gk[3];
-                gk[2] = by[1] - by[0];
-                const T s = fma(dl[2], gk[2], by[0]);
-                gk[1] = fma(dl[2], dy[1] - dy[0], dy[0]);
-                gk[0] = fma(dl[2], ex[1] - ex[0], ex[0]);
-                acc[NV - 1] += s * q.w;                           // d_out_weight,   src/raster_pullback.jl:57
-                const T f = pose.ow * q.w;                        // :60
-                T scaled[3];
-#pragma unroll
-                for (int n = 0; n < 3; ++n) {
-                    scaled[n] = (f * gk[n]) * grid.scale[n];      // :67
-                    acc[NR + n] += scaled[n];                     // d_translation, :68
-                }
-                T dpt[3] = {T(0), T(0), T(0)};
-#pragma unroll
-                for (int jj = 0; jj < N_IN; ++jj) {
-                    T d = T(0);
-#pragma unroll
-                    for (int n = 0; n < 3; ++n) {
-                        acc[n + jj * 3] += scaled[n] * x[jj];     // d_rotation, :69
-                        d += pose.R[n][jj] * scaled[n];           // R' * scaled, :70
-                    }
-                    dpt[jj] = d;
-                }
-                // pose-sum of d_points (:71, :141) and d_point_weight (:58, :146): one 16-byte reduction into the packed,
-                // L2-resident buffer (sorted point order)
-                red_add4(acc4 + idx, dpt[0], dpt[1], dpt[2], s * pose.ow);
-            }
+        for (int yz = 0; yz < 4; ++yz) {
+            dx[yz] = G[2 * yz + 1] - G[2 * yz];
+            ax[yz] = fma(dl[0], dx[yz], G[2 * yz]);
         }
-        __syncwarp();
-        if (lane == 0) {
-            if (USE_TMA) mbar_arrive(&tile_empty[stage]);           // this warp is done with the stage
-            if (j == kBatch - 1) mbar_arrive(&ring.empty[batch & 1]);
+        T by[2], dy[2], ex[2];
+#pragma unroll
+        for (int z = 0; z < 2; ++z) {
+            dy[z] = ax[2 * z + 1] - ax[2 * z];
+            by[z] = fma(dl[1], dy[z], ax[2 * z]);
+            ex[z] = fma(dl[1], dx[2 * z + 1] - dx[2 * z], dx[2 * z]);
+        }
+        T gk[3];
+        gk[2] = by[1] - by[0];
+        const T s = fma(dl[2], gk[2], by[0]);
+        gk[1] = fma(dl[2], dy[1] - dy[0], dy[0]);
+        gk[0] = fma(dl[2], ex[1] - ex[0], ex[0]);
+        acc[NV - 1] += s * q.w;                           // d_out_weight,   src/raster_pullback.jl:57
+        const T f = pose.ow * q.w;                        // :60
+        T scaled[3];
+#pragma unroll
+        for (int n = 0; n < 3; ++n) {
+            scaled[n] = (f * gk[n]) * grid.scale[n];      // :67
+            acc[NR + n] += scaled[n];                     // d_translation, :68
+        }
+        T dpt[3] = {T(0), T(0), T(0)};
+#pragma unroll
+        for (int jj = 0; jj < N_IN; ++jj) {
+            T d = T(0);
+#pragma unroll
+            for (int n = 0; n < 3; ++n) {
+                acc[n + jj * 3] += scaled[n] * x[jj];     // d_rotation, :69
+                d += pose.R[n][jj] * scaled[n];           // R' * scaled, :70
+            }
+            dpt[jj] = d;
+        }
+        // pose-sum of d_points (:71, :141) and d_point_weight (:58, :146): one 16-byte reduction into the packed,
+        // L2-resident buffer (sorted point order)
+        red_add4(acc4 + idx_c, dpt[0], dpt[1], dpt[2], s * pose.ow);
+    }
+    // per-pose sums of this CTA: warp shuffles, then one line of shared memory per warp, then one REDG per value
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc[v] = warp_sum(acc[v]);
+    bg_part = warp_sum(bg_part);
+    if (lane == 0) {
+#pragma unroll
+        for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
+        red[warp][NV] = bg_part;
+    }
+    __syncthreads();
+    if (threadIdx.x <= NV) {
+        const int v = threadIdx.x;
+        T r = T(0);
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) r += red[w][v];
+        if (v == NV) { if (d_background) red_add(d_background + b, r); }
+        else if (r != T(0)) {
+            if (v < NR) red_add(d_rotation + b * NR + v, r);
+            else if (v < NR + 3) red_add(d_translation + b * 3 + (v - NR), r);
+            else if (d_out_weight) red_add(d_out_weight + b, r);
         }
     }
-    if (cur_bl >= 0) flush_pose();
 }
 
 // 6. packed, sorted-order gradients -> d_points (N_in, P) and d_point_weight (P) in the caller's point order
