@@ -639,7 +639,7 @@ static int forward_tile3d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
         rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
         if (rc != DPR_OK) return rc;
         LaunchScope scope("fwd_tile3d", a.stream);
-        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, smem, a.stream>>>(pts4, entries, cnt, a.rotation, a.translation, a.background,
+        kern<<<dim3((unsigned)pl.tg.nt[0], (unsigned)pl.tg.nt[1], (unsigned)(pl.tg.nt[2] * nb)), t3::kThreads, smem, a.stream>>>(pts4, entries, cnt, a.rotation, a.translation, a.background,
                                                                               a.out_weight, a.out, grid, pl.tg, b0, pw_stats, a.P, fixed_bits);
     }
     DPR_CUDA_TRY(cudaGetLastError());

@@ -401,7 +401,7 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
         const int rcs = opt_in_smem_once(kern, tile_bytes, dev);
         if (rcs != DPR_OK) return rcs;
         LaunchScope scope("pullback_tile3d", a.stream);
-        kern<<<(unsigned)(nb * pl.tg.n_tiles), t3::kThreads, tile_bytes, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation,
+        kern<<<dim3((unsigned)pl.tg.nt[0], (unsigned)pl.tg.nt[1], (unsigned)(pl.tg.nt[2] * nb)), t3::kThreads, tile_bytes, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation,
                                                                                     a.translation, a.out_weight, acc4, a.d_rotation,
                                                                                     a.d_translation, a.d_background, a.d_out_weight, grid,
                                                                                     pl.tg, b0);

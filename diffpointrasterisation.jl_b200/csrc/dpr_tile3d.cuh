@@ -441,10 +441,9 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
     T* tile = reinterpret_cast<T*>(smem_raw);
     __shared__ SlotTable tab;
     __shared__ long long scratch[kThreads / 32];
-    const int bl = blockIdx.x / tg.n_tiles;
-    const int t = blockIdx.x - bl * tg.n_tiles;
-    const int row = tg.nt[0] * tg.nt[1];
-    const int tz = t / row, ty = (t - tz * row) / tg.nt[0], tx = t - tz * row - ty * tg.nt[0];
+    // launch grid (nt0, nt1, nt2 * poses): one division instead of four
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int bl = blockIdx.z / tg.nt[2], tz = blockIdx.z - bl * tg.nt[2];
     const int64_t b = b0 + bl;
     build_slot_table(tab, cnt, tg, bl, tx, ty, tz);
 
@@ -659,6 +658,34 @@ __device__ __forceinline__ void tma_load_tile4d(void* dst, const CUtensorMap* ma
         "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
         : "memory");
 }
+// Sum 16 values across the warp.  Returns, in lane L, the total of value index L >> 1.
+template <typename T>
+__device__ __forceinline__ T butterfly16(T (&a)[16], int lane) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {          // lanes with bit 4 keep the upper half of the indices
+        const bool hi = lane & 16;
+        const T send = hi ? a[i] : a[i + 8], keep = hi ? a[i + 8] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const bool hi = lane & 8;
+        const T send = hi ? a[i] : a[i + 4], keep = hi ? a[i + 4] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const bool hi = lane & 4;
+        const T send = hi ? a[i] : a[i + 2], keep = hi ? a[i + 2] : a[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const bool hi = lane & 2;
+        const T send = hi ? a[0] : a[1], keep = hi ? a[1] : a[0];
+        a[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+}
 __device__ __forceinline__ void red_add4(Pt4<float>* addr, float a, float b, float c, float d) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
@@ -685,10 +712,9 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
     __shared__ SlotTable tab;
     __shared__ __align__(8) uint64_t bar;
     __shared__ T red[kThreads / 32][NV + 1];
-    const int bl = blockIdx.x / tg.n_tiles;
-    const int t = blockIdx.x - bl * tg.n_tiles;
-    const int row = tg.nt[0] * tg.nt[1];
-    const int tz = t / row, ty = (t - tz * row) / tg.nt[0], tx = t - tz * row - ty * tg.nt[0];
+    // launch grid (nt0, nt1, nt2 * poses): one division instead of four
+    const int tx = blockIdx.x, ty = blockIdx.y;
+    const int bl = blockIdx.z / tg.nt[2], tz = blockIdx.z - bl * tg.nt[2];
     const int64_t b = b0 + bl;
     const int ox = tx * TX, oy = ty * TY, oz = tz * TZ;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -843,14 +869,15 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
         // L2-resident buffer (sorted point order)
         red_add4(acc4 + idx_c, dpt[0], dpt[1], dpt[2], s * pose.ow);
     }
-    // per-pose sums of this CTA: warp shuffles, then one line of shared memory per warp, then one REDG per value
+    // per-pose sums of this CTA: a transposing butterfly (every shuffle step halves the number of live values: 16 shuffles
+    // for 16 values instead of 5 each - the plain reduction was 22 % of this kernel's instructions), one line of shared
+    // memory per warp, then one REDG per value
+    {
+        T vals[16];
 #pragma unroll
-    for (int v = 0; v < NV; ++v) acc[v] = warp_sum(acc[v]);
-    bg_part = warp_sum(bg_part);
-    if (lane == 0) {
-#pragma unroll
-        for (int v = 0; v < NV; ++v) red[warp][v] = acc[v];
-        red[warp][NV] = bg_part;
+        for (int v = 0; v < 16; ++v) vals[v] = v < NV ? acc[v] : (v == NV ? bg_part : T(0));
+        const T r = butterfly16(vals, lane);            // lane L holds the warp total of value L >> 1 (both lanes of a pair)
+        if ((lane & 1) == 0 && (lane >> 1) <= NV) red[warp][lane >> 1] = r;
     }
     __syncthreads();
     if (threadIdx.x <= NV) {
@@ -910,7 +937,9 @@ inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int s
     int64_t group = B;
     if (group > ((int64_t)1 << 27) / P) group = ((int64_t)1 << 27) / P;
     if (group > ((int64_t)1 << 24) / (n_tiles * 8)) group = ((int64_t)1 << 24) / (n_tiles * 8);
-    if (group > 65535) group = 65535;
+    if (group > 65535) group = 65535;                                   // gridDim.y of the binning kernels
+    if (pl.tg.nt[1] > 65535 || pl.tg.nt[2] > 65535) return pl;          // gridDim.y / gridDim.z of the tile kernels
+    if (group * pl.tg.nt[2] > 65535) group = 65535 / pl.tg.nt[2];
     if (group < 1) group = 1;
     if (group * n_tiles > (int64_t)0x7fffffff) return pl;
     pl.group = group;
