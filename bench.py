@@ -214,6 +214,125 @@ def run_reference(args, cfg):
     emit(line)
 
 
+class Workload:
+    """One configuration resident on one GPU: inputs, outputs, the step (forward + pullback), its measurements."""
+
+    def __init__(self, name, cfg, rank, dev, comm=None):
+        import torch
+        import dpr_b200
+        from dpr_b200 import sharded
+        self.name, self.cfg, self.dev = name, cfg, dev
+        self.td = torch.float32 if cfg["dtype"] == "f32" else torch.float64
+        seed = 1000 + int(name[-1]) + (100 if name.startswith("readme") else 0)
+        self.inputs = synth_inputs(cfg, seed, rank)
+        f = lambda a: None if a is None else dpr_b200.fortran(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
+        i = self.inputs
+        self.points = f(i["points"])
+        self.background, self.out_weight, self.point_weight = f(i["background"]), f(i["out_weight"]), f(i["point_weight"])
+        # Two pose sets, alternated step by step: like an optimiser loop, no step sees the poses of the step before, so
+        # nothing a step computes (the 3-d path's point bins, DPR_OPT_BINNING_CACHE) can be left over from the previous
+        # one - only the pullback of a step may reuse what the forward of the SAME step binned (the rrule's call order).
+        other = synth_inputs(cfg, seed + 50_000, rank)
+        self.poses = [(f(i["rotation"]), f(i["translation"])), (f(other["rotation"]), f(other["translation"]))]
+        grid, B = tuple(cfg["grid"]), cfg["B"]
+        gen = torch.Generator(device=dev).manual_seed(seed * 31 + rank)
+        self.ds_dout = dpr_b200.empty_f(grid + (B,), self.td, dev)
+        self.ds_dout.normal_(generator=gen)
+        self.do_fwd = "fwd" in cfg["ops"]
+        self.out = dpr_b200.empty_f(grid + (B,), self.td, dev) if self.do_fwd else None
+        self.drv = sharded.PoseShardedRaster(comm=comm)
+        self.n_step = 0
+        self.last = None
+
+    def step(self):
+        import dpr_b200
+        rot, tr = self.poses[self.n_step & 1]
+        self.n_step += 1
+        if self.do_fwd:
+            dpr_b200.raster_(self.out, self.points, rot, tr, self.background, self.out_weight, self.point_weight)
+        self.last, _ = self.drv.raster_pullback_(self.ds_dout, self.points, rot, tr, self.background, self.out_weight,
+                                                 self.point_weight)
+        return self.last
+
+    def measure(self, steps, warmup, sync_all, world, profiled_steps=None):
+        """Times `steps` steps with CUDA events (no per-kernel instrumentation inside the timed region), then a second,
+        shorter pass with the library's per-launch events for the kernel breakdown."""
+        import torch
+        import torch.distributed as dist
+        import dpr_b200
+        from dpr_b200 import _lib
+        cfg = self.cfg
+        for _ in range(warmup):
+            self.step()
+        sync_all()
+        launches0 = dpr_b200.kernel_launch_count()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(steps):
+            self.step()
+        ev[1].record()
+        sync_all()
+        local_ms = ev[0].elapsed_time(ev[1]) / steps
+        launches = dpr_b200.kernel_launch_count() - launches0
+        paths = (dpr_b200.last_path(0) if self.do_fwd else "none", dpr_b200.last_path(1))
+        ms_per_step, per_rank = local_ms, None
+        if world > 1:
+            t = torch.tensor([local_ms], dtype=torch.float64, device=self.dev)
+            allt = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allt, t)
+            per_rank = [float(x.item()) for x in allt]
+            ms_per_step = max(per_rank)
+        # ---- kernel breakdown: a separate pass, every launch bracketed by events on its stream -------------------
+        n_prof = min(steps, profiled_steps or 10)
+        _lib.profile_enable(True)
+        for _ in range(n_prof):
+            self.step()
+        sync_all()
+        records = _lib.profile_records()
+        _lib.profile_enable(False)
+        kernels = {}
+        for name, ms in records:
+            kernels.setdefault(name, []).append(ms)
+        kernel_ms = {k: sum(v) / n_prof for k, v in kernels.items()}              # per step (all launches of the kernel)
+        kernel_launch_ms = {k: sum(v) / len(v) for k, v in kernels.items()}       # per launch
+        launches_per_step = {k: len(v) / n_prof for k, v in kernels.items()}
+        fwd_bytes, bwd_bytes = algorithmic_bytes(cfg)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+        else:
+            peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+        fwd_names = [k for k in kernel_ms if k.startswith("fwd_")]
+        bwd_names = [k for k in kernel_ms if k.startswith("pullback_")]
+        cand = {}
+        if fwd_names and self.do_fwd:
+            cand[max(fwd_names, key=kernel_ms.get)] = fwd_bytes
+        if bwd_names:
+            cand[max(bwd_names, key=kernel_ms.get)] = bwd_bytes
+        dom = max(cand, key=lambda k: kernel_ms[k])
+        bytes_per_launch = cand[dom] / launches_per_step[dom]
+        achieved = bytes_per_launch / (kernel_launch_ms[dom] * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            traffic = json.load(open(tpath)).get(self.name, {}).get(dom)
+        step_bytes = (fwd_bytes if self.do_fwd else 0) + bwd_bytes
+        roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
+                        algorithmic_bytes_per_launch=bytes_per_launch, kernel_ms=kernel_launch_ms[dom],
+                        launches_per_step=launches_per_step[dom], peak_source=peak_src,
+                        whole_step=dict(algorithmic_bytes=step_bytes, achieved=step_bytes / (ms_per_step * 1e-3) / 1e9,
+                                        frac=step_bytes / (ms_per_step * 1e-3) / 1e9 / peak))
+        return dict(ms_per_step=ms_per_step, per_rank_ms=per_rank, kernels_ms=kernel_ms, launches=launches, paths=paths,
+                    roofline=roofline, splats_per_s=cfg["P"] * cfg["B"] * world / (ms_per_step * 1e-3),
+                    fwd_splats_per_s=(cfg["P"] * cfg["B"] * world / (sum(v for k, v in kernel_ms.items() if k.startswith("fwd_") or k == "fill_background") * 1e-3))
+                    if self.do_fwd and fwd_names else None)
+
+    def free(self):
+        import torch
+        self.__dict__.clear()
+        torch.cuda.empty_cache()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -221,9 +340,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the other BASELINE configurations (other_configs block)")
     ap.add_argument("--cpu-poses", type=int, default=2048, help="poses in the cpu_baseline sample")
     ap.add_argument("--ref-poses", type=int, default=512, help="poses per step of the --impl reference arm")
     args = ap.parse_args()
@@ -256,31 +376,12 @@ def main():
         except Exception:
             pass
         dist.init_process_group("nccl", device_id=dev)
-    td = torch.float32 if cfg["dtype"] == "f32" else torch.float64
-    seed = 1000 + int(args.config[-1]) + (100 if args.config.startswith("readme") else 0)
-    inputs = synth_inputs(cfg, seed, rank)
-    f = lambda a: None if a is None else dpr_b200.fortran(torch.from_numpy(np.ascontiguousarray(a)).to(dev))
-    points, rotation, translation = f(inputs["points"]), f(inputs["rotation"]), f(inputs["translation"])
-    background, out_weight, point_weight = f(inputs["background"]), f(inputs["out_weight"]), f(inputs["point_weight"])
-    grid, P, B = tuple(cfg["grid"]), cfg["P"], cfg["B"]
-    gen = torch.Generator(device=dev).manual_seed(seed * 31 + rank)
-    ds_dout = dpr_b200.empty_f(grid + (B,), td, dev)
-    ds_dout.normal_(generator=gen)
-    out = dpr_b200.empty_f(grid + (B,), td, dev)
     comm, comm_kind = None, "none"
     if world > 1:
         try:
             comm, comm_kind = sharded.DprComm(dev), "dpr_comm_allreduce_sum (NCCL via libdpr.so)"
         except Exception as e:   # NCCL could not be resolved inside the library: torch.distributed does the all-reduce
             comm, comm_kind = None, f"torch.distributed all_reduce ({type(e).__name__})"
-    drv = sharded.PoseShardedRaster(comm=comm)
-    do_fwd = "fwd" in cfg["ops"]
-
-    def step():
-        if do_fwd:
-            dpr_b200.raster_(out, points, rotation, translation, background, out_weight, point_weight)
-        res, _ = drv.raster_pullback_(ds_dout, points, rotation, translation, background, out_weight, point_weight)
-        return res
 
     def sync_all():
         torch.cuda.synchronize(dev)
@@ -288,72 +389,61 @@ def main():
             dist.barrier()
             torch.cuda.synchronize(dev)
 
-    for _ in range(args.warmup):
-        step()
-    sync_all()
-    launches0 = dpr_b200.kernel_launch_count()
-    _lib.profile_enable(True)
+    wl = Workload(args.config, cfg, rank, dev, comm)
+    P, B, grid = cfg["P"], cfg["B"], tuple(cfg["grid"])
+    td = wl.td
+    do_fwd = wl.do_fwd
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-    ev[0].record()
-    for _ in range(args.steps):
-        step()
-    ev[1].record()
-    sync_all()
+    head = wl.measure(args.steps, args.warmup, sync_all, world)
     sampler.stop_flag = True
-    total_ms = ev[0].elapsed_time(ev[1])
-    records = _lib.profile_records()
-    _lib.profile_enable(False)
-    paths = (dpr_b200.last_path(0), dpr_b200.last_path(1))      # of the timed steps (the e2e leg below runs pose chunks)
-    launches = dpr_b200.kernel_launch_count() - launches0
     sampler.join(timeout=1.0)
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
+    ms_per_step = head["ms_per_step"]
     splats = P * B * world
     value = splats / (ms_per_step * 1e-3)
 
-    kernels = {}
-    for name, ms in records:
-        kernels.setdefault(name, []).append(ms)
-    kernel_ms = {k: sum(v) / args.steps for k, v in kernels.items()}            # per step (all launches of the kernel)
-    kernel_launch_ms = {k: sum(v) / len(v) for k, v in kernels.items()}         # per launch
-    launches_per_step = {k: len(v) / args.steps for k, v in kernels.items()}
-    fwd_bytes, bwd_bytes = algorithmic_bytes(cfg)
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
-    else:
-        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
-    fwd_names = [k for k in kernel_ms if k.startswith("fwd_")]
-    bwd_names = [k for k in kernel_ms if k.startswith("pullback_")]
-    cand = {}
-    if fwd_names:
-        cand[max(fwd_names, key=kernel_ms.get)] = fwd_bytes
-    if bwd_names:
-        cand[max(bwd_names, key=kernel_ms.get)] = bwd_bytes
-    dom = max(cand, key=lambda k: kernel_ms[k])
-    bytes_per_launch = cand[dom] / launches_per_step[dom]
-    achieved = bytes_per_launch / (kernel_launch_ms[dom] * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get(args.config, {}).get(dom)
-    roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    traffic=traffic, algorithmic_bytes_per_launch=bytes_per_launch, kernel_ms=kernel_launch_ms[dom],
-                    launches_per_step=launches_per_step[dom], peak_source=peak_src,
-                    whole_step=dict(algorithmic_bytes=(fwd_bytes if do_fwd else 0) + bwd_bytes,
-                                    achieved=((fwd_bytes if do_fwd else 0) + bwd_bytes) / (ms_per_step * 1e-3) / 1e9,
-                                    frac=((fwd_bytes if do_fwd else 0) + bwd_bytes) / (ms_per_step * 1e-3) / 1e9 / peak))
+    # ---- multi-GPU: cost of the collective and a check of what it produced (outside the timed region) ----------------
+    multi = None
+    if world > 1:
+        n_in = cfg["n_in"]
+        packed = wl.drv.packed_buffer(n_in, P, td, dev)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        reps = 20
+        sync_all()
+        ev[0].record()
+        for _ in range(reps):
+            if comm is not None:
+                comm.all_reduce_(packed)
+            else:
+                dist.all_reduce(packed)
+        ev[1].record()
+        sync_all()
+        t = torch.tensor([ev[0].elapsed_time(ev[1]) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        allreduce_ms = float(t.item())
+        # the all-reduced [d_points; d_point_weight] must equal the sum of the ranks' local pullbacks
+        rot, tr = wl.poses[0]
+        local = dpr_b200.raster_pullback_(wl.ds_dout, wl.points, rot, tr, wl.background, wl.out_weight, wl.point_weight)
+        local_packed = torch.cat([local.points.t().reshape(-1), local.point_weight.reshape(-1)])
+        gathered = [torch.empty_like(local_packed) for _ in range(world)]
+        dist.all_gather(gathered, local_packed)
+        want = torch.stack(gathered).to(torch.float64).sum(0)
+        wl.n_step = 0
+        wl.step()                                   # poses[0] again, through the sharded driver (with its all-reduce)
+        got = wl.drv.packed_buffer(n_in, P, td, dev).to(torch.float64)
+        err = float(((got - want).norm() / want.norm().clamp_min(1e-300)).item())
+        tol = 1e-5 if cfg["dtype"] == "f32" else 1e-10
+        multi = dict(allreduce_ms=allreduce_ms, allreduce_bytes=packed.numel() * packed.element_size(),
+                     step_ms_min=min(head["per_rank_ms"]), step_ms_max=max(head["per_rank_ms"]), per_rank_step_ms=head["per_rank_ms"],
+                     allreduce_check=dict(rel_l2_vs_sum_of_rank_partials=err, tol=tol, ok=bool(err <= tol)))
 
     # ---- end to end through the host-buffer C ABI (H2D of inputs and D2H of results inside the timed region) ----
     e2e = None
     if not args.no_e2e:
         lib = _lib.load()
         suf = cfg["dtype"]
+        points, (rotation, translation) = wl.points, wl.poses[0]
+        background, out_weight, point_weight, ds_dout = wl.background, wl.out_weight, wl.point_weight, wl.ds_dout
         pin = lambda t: None if t is None else t.detach().cpu().pin_memory()
         h = dict(points=pin(points.t().contiguous()), rotation=pin(rotation.permute(2, 1, 0).contiguous()),
                  translation=pin(translation.t().contiguous()), background=pin(background), out_weight=pin(out_weight),
@@ -377,10 +467,13 @@ def main():
                 n_in, n_out, garr, P, B, p(h["ds_dout"]), p(h["points"]), p(h["rotation"]), p(h["translation"]),
                 p(h["out_weight"]), p(h["point_weight"]), p(g["dp"]), p(g["drot"]), p(g["dtr"]), p(g["dbg"]), p(g["dow"]),
                 p(g["dpw"])))
-            if world > 1:   # pose-sum across ranks: host -> device -> NCCL -> host
+            if world > 1:   # pose-sum across ranks: host -> device -> the library's collective -> host
                 packed_dev[: n_in * P].copy_(g["dp"], non_blocking=True)
                 packed_dev[n_in * P:].copy_(g["dpw"], non_blocking=True)
-                dist.all_reduce(packed_dev)
+                if comm is not None:
+                    comm.all_reduce_(packed_dev)
+                else:
+                    dist.all_reduce(packed_dev)
                 g["dp"].copy_(packed_dev[: n_in * P], non_blocking=True)
                 g["dpw"].copy_(packed_dev[n_in * P:], non_blocking=True)
                 torch.cuda.synchronize(dev)
@@ -401,18 +494,40 @@ def main():
         h2d = (in_small if do_fwd else 0) + in_small + nbytes(h["ds_dout"])
         d2h = nbytes(h_out) + sum(nbytes(v) for v in g.values())
         e2e = dict(value=splats / e2e_s, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h, ms_per_step=1e3 * e2e_s,
-                   steps=args.e2e_steps, api="dpr_raster_forward_host_* + dpr_raster_pullback_host_* (pinned host buffers)")
+                   steps=args.e2e_steps, api="dpr_raster_forward_host_* + dpr_raster_pullback_host_* (pinned host buffers)",
+                   link_gbs=(h2d + d2h) / e2e_s / 1e9)
         lib.dpr_host_release()
+        del h, h_out, g
 
     cpu_baseline = None
     if world == 1 and rank == 0 and not args.no_cpu:
         threads = host_threads()
         n_poses = min(B, args.cpu_poses)
-        cpu_port_time(cfg, inputs, min(n_poses, threads), threads)  # warm the threads
-        tf, tb = min((cpu_port_time(cfg, inputs, n_poses, threads) for _ in range(2)), key=sum)   # best of two passes
+        cpu_port_time(cfg, wl.inputs, min(n_poses, threads), threads)  # warm the threads
+        tf, tb = min((cpu_port_time(cfg, wl.inputs, n_poses, threads) for _ in range(2)), key=sum)   # best of two passes
         cpu_baseline = dict(value=P * n_poses / (tf + tb), unit=UNIT, cores=threads, kind="port",
                             sample=f"first {n_poses} of {B} poses, all {P} points, one pass (fwd {tf:.2f}s + bwd {tb:.2f}s)",
                             fwd_splats_per_s=(P * n_poses / tf) if tf else None, bwd_splats_per_s=P * n_poses / tb)
+
+    # ---- every other BASELINE configuration, ten steps each (device-resident), so the driver's record carries them ------
+    others = None
+    if not args.no_others and args.config == "cfg2":
+        wl.free()
+        others = {}
+        # one GPU: all of them; several ranks: config 5, the one BASELINE.json shards over 8 GPUs (2048 poses per rank)
+        names = ("cfg1", "cfg3", "cfg4", "cfg5") if world == 1 else ("cfg5",)
+        for name in names:
+            try:
+                w2 = Workload(name, CONFIGS[name], rank, dev, comm)
+                r = w2.measure(10, 3, sync_all, world)
+                others[name] = dict(workload=CONFIGS[name]["label"], ops=CONFIGS[name]["ops"], ms_per_step=r["ms_per_step"],
+                                    splats_per_s=r["splats_per_s"], kernels_ms=r["kernels_ms"],
+                                    roofline_frac=r["roofline"]["frac"], roofline_kernel=r["roofline"]["kernel"],
+                                    whole_step_frac=r["roofline"]["whole_step"]["frac"], forward_path=r["paths"][0],
+                                    pullback_path=r["paths"][1], per_rank_step_ms=r["per_rank_ms"])
+                w2.free()
+            except Exception as e:      # one configuration failing must not lose the headline line
+                others[name] = dict(error=f"{type(e).__name__}: {e}"[:300])
 
     if rank == 0:
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
@@ -422,9 +537,12 @@ def main():
                                 parallelism=f"pose-sharded x{world}, points replicated, 1 all-reduce of d_points+d_point_weight",
                                 collective=comm_kind,
                                 l2="inputs larger than L2 (out and ds_dout are 1.07 GB each per step; no flush needed)",
-                                forward_path=paths[0], pullback_path=paths[1]),
-                    kernels_ms=kernel_ms, fwd_splats_per_s=(P * B * world / (sum(kernel_ms[k] for k in kernel_ms if k.startswith("fwd_") or k == "fill_background") * 1e-3)) if do_fwd else None,
-                    roofline=roofline, cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=launches, clocks=sampler.result())
+                                poses="two pose sets alternate step by step (no step repeats the previous step's inputs)",
+                                timing="headline: CUDA events around the steps, no per-kernel instrumentation; kernels_ms: a separate pass",
+                                forward_path=head["paths"][0], pullback_path=head["paths"][1]),
+                    kernels_ms=head["kernels_ms"], fwd_splats_per_s=head["fwd_splats_per_s"],
+                    roofline=head["roofline"], cpu_baseline=cpu_baseline, e2e=e2e, gpu_launches=head["launches"],
+                    clocks=sampler.result(), multi_gpu=multi, other_configs=others)
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -24,7 +24,7 @@ SYMBOLS = [
     "dpr_comm_unique_id", "dpr_comm_init_rank", "dpr_comm_destroy", "dpr_comm_allreduce_sum_f32", "dpr_comm_allreduce_sum_f64",
 ]
 
-OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM, OPT_POINT_SORT, OPT_TILE3D_TMA = range(8)
+OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM, OPT_POINT_SORT, OPT_TILE3D_TMA, OPT_BINNING_CACHE = range(9)
 OP_FORWARD, OP_PULLBACK = 0, 1
 
 _lib = None
@@ -40,9 +40,8 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        _build.build()
-    lib = ctypes.CDLL(LIB_PATH)
+    _build.build()          # no-op when libdpr.so is newer than every source it is built from (a stale binary would be
+    lib = ctypes.CDLL(LIB_PATH)     # loaded silently against a newer header / SYMBOLS list otherwise)
     c_i, c_i64, c_p, c_sz = ctypes.c_int, ctypes.c_int64, ctypes.c_void_p, ctypes.c_size_t
     lib.dpr_version.restype = c_i
     lib.dpr_status_string.restype = ctypes.c_char_p
@@ -91,6 +90,9 @@ def load() -> ctypes.CDLL:
         f.argtypes = [c_p, c_p, c_i64, c_p]
     lib.dpr_last_path.restype = ctypes.c_char_p
     lib.dpr_last_path.argtypes = [c_i]
+    # The mirror owns its workspaces (interface._workspace: persistent per device and stream, header zeroed on allocation),
+    # which is what DPR_OPT_BINNING_CACHE asks of a caller
+    lib.dpr_set_option(OPT_BINNING_CACHE, 1)
     _lib = lib
     return lib
 

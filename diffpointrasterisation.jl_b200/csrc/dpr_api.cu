@@ -230,6 +230,7 @@ static int arena_reserve(void*& ptr, size_t& have, size_t want) {
     ptr = nullptr; have = 0;
     want = (want + 4095) / 4096 * 4096;
     DPR_CUDA_TRY(cudaMalloc(&ptr, want));
+    DPR_CUDA_TRY(cudaMemset(ptr, 0, 256));      // a kernel workspace starts with a clean binning-cache header (include/dpr.h)
     have = want;
     return DPR_OK;
 }
@@ -569,6 +570,7 @@ int dpr_set_option(int option, int64_t value) {
         case DPR_OPT_FORWARD_ACCUM: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.forward_accum = value; return DPR_OK;
         case DPR_OPT_POINT_SORT: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.point_sort = value; return DPR_OK;
         case DPR_OPT_TILE3D_TMA: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.tile3d_tma = value; return DPR_OK;
+        case DPR_OPT_BINNING_CACHE: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.binning_cache = value; return DPR_OK;
         default: return DPR_ERR_BAD_OPTION;
     }
 }
@@ -582,6 +584,7 @@ int64_t dpr_get_option(int option) {
         case DPR_OPT_FORWARD_ACCUM: return g_tuning.forward_accum;
         case DPR_OPT_POINT_SORT: return g_tuning.point_sort;
         case DPR_OPT_TILE3D_TMA: return g_tuning.tile3d_tma;
+        case DPR_OPT_BINNING_CACHE: return g_tuning.binning_cache;
         default: return -1;
     }
 }

@@ -615,7 +615,10 @@ template <typename T, int N_IN>
 static int forward_tile3d(const ForwardArgs<T>& a, const DeviceInfo& dev, const t3::Plan& pl) {
     const Grid<T, 3> grid = t3::make_grid3<T>(a.grid);
     char* ws = static_cast<char*>(a.workspace);
-    int rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, false, dev, a.stream);
+    t3::CacheCtl cache;
+    int rc = t3::cache_begin<T>(cache, ws, pl, N_IN, a.grid, a.points, a.point_weight, a.rotation, a.translation, a.P, a.B, dev, a.stream);
+    if (rc != DPR_OK) return rc;
+    rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, cache, dev, a.stream);
     if (rc != DPR_OK) return rc;
     const size_t smem = sizeof(T) * (size_t)t3::FwdTile<T>::SIZE;
     auto kern = t3::fwd_tile3d_kernel<T, N_IN>;
@@ -636,11 +639,11 @@ static int forward_tile3d(const ForwardArgs<T>& a, const DeviceInfo& dev, const 
     }
     for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
         const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
-        rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
+        rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, cache, a.stream);
         if (rc != DPR_OK) return rc;
         LaunchScope scope("fwd_tile3d", a.stream);
         kern<<<dim3((unsigned)pl.tg.nt[0], (unsigned)pl.tg.nt[1], (unsigned)(pl.tg.nt[2] * nb)), t3::kThreads, smem, a.stream>>>(pts4, entries, cnt, a.rotation, a.translation, a.background,
-                                                                              a.out_weight, a.out, grid, pl.tg, b0, pw_stats, a.P, fixed_bits);
+                                                                              a.out_weight, a.out, grid, pl.tg, b0, pw_stats, a.P, fixed_bits, cache.valid);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     set_last_path(DPR_OP_FORWARD, fixed_bits ? "tile3d_binned_fixed" : "tile3d_binned");
@@ -651,9 +654,12 @@ template <typename T>
 int forward_dispatch(const ForwardArgs<T>& a, const DeviceInfo& dev) {
     const int64_t algo = tuning().forward_algo;
     if (a.n_out == 3 && a.n_in == 3 && algo != 1 && a.P > 0 && a.B > 0 && (algo == 3 || t3::worthwhile(a.grid, a.P, a.B))) {
-        const t3::Plan pl = t3::make_plan(a.n_in, a.grid, a.P, a.B, (int)sizeof(T), false);
+        const t3::Plan pl = t3::make_plan(a.n_in, a.grid, a.P, a.B, (int)sizeof(T));
         if (pl.ok && a.workspace && a.workspace_bytes >= pl.total) return forward_tile3d<T, 3>(a, dev, pl);
     }
+    // every other path may overwrite a workspace that holds cached bins of the 3-d tile path: un-mark them first
+    if (tuning().binning_cache == 1 && a.workspace && a.workspace_bytes >= 256)
+        DPR_CUDA_TRY(cudaMemsetAsync(static_cast<char*>(a.workspace) + t3::cache_valid_offset(), 0, sizeof(unsigned long long), a.stream));
     if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && algo != 1 && a.P > 0 && a.B > 0) {
         TileParams<T> tp;
         size_t smem = 0;
@@ -686,7 +692,7 @@ size_t forward_workspace_bytes(int n_in, int n_out, const int64_t* grid, int64_t
     const size_t radial = P >= 8192 ? make_radial_plan(P, 256).total + 256 : 0;   // radial kernel: large clouds only
     size_t need = morton > radial ? morton : radial;
     if (n_out == 3 && n_in == 3 && grid) {     // tile-binned 3-d path: sorted copy, keys, counters, P x poses entries
-        const t3::Plan pl = t3::make_plan(n_in, grid, P, B, sizeof_T, false);
+        const t3::Plan pl = t3::make_plan(n_in, grid, P, B, sizeof_T);
         if (pl.ok && (tuning().forward_algo == 3 || t3::worthwhile(grid, P, B)) && pl.total > need) need = pl.total;
     }
     return need;

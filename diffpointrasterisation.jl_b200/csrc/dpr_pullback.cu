@@ -371,8 +371,12 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
         LaunchScope scope("zero_gradients", a.stream);
         zero_buffers_kernel<<<8, 256, 0, a.stream>>>(z);
     }
-    int rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, true, dev, a.stream);
+    t3::CacheCtl cache;
+    int rc = t3::cache_begin<T>(cache, ws, pl, N_IN, a.grid, a.points, a.point_weight, a.rotation, a.translation, a.P, a.B, dev, a.stream);
     if (rc != DPR_OK) return rc;
+    rc = t3::presort<T, N_IN>(a.points, a.point_weight, a.P, ws, pl, cache, dev, a.stream);
+    if (rc != DPR_OK) return rc;
+    DPR_CUDA_TRY(cudaMemsetAsync(ws + pl.off_acc4, 0, sizeof(T) * 4 * (size_t)a.P, a.stream));     // packed pose-sum accumulator
     // tensor-map TMA for the tile loads when the volume qualifies (16-byte rows and base): one 4-d map over
     // (g0, g1, g2, B), box = one tile.  Tile origins are multiples of 32 cells, which satisfies the 16-byte box-start rule
     // (dpr_tile3d.cuh); DPR_OPT_TILE3D_TMA = 1 forces the cooperative loads.
@@ -404,12 +408,12 @@ static int pullback_tile3d(const PullbackArgs<T>& a, const DeviceInfo& dev, cons
         kern<<<dim3((unsigned)pl.tg.nt[0], (unsigned)pl.tg.nt[1], (unsigned)(pl.tg.nt[2] * nb)), t3::kThreads, tile_bytes, a.stream>>>(map, a.ds_dout, pts4, entries, cnt, a.rotation,
                                                                                     a.translation, a.out_weight, acc4, a.d_rotation,
                                                                                     a.d_translation, a.d_background, a.d_out_weight, grid,
-                                                                                    pl.tg, b0);
+                                                                                    pl.tg, b0, cache.valid);
         return DPR_OK;
     };
     for (int64_t b0 = 0; b0 < a.B; b0 += pl.group) {
         const int64_t nb = (b0 + pl.group < a.B) ? pl.group : a.B - b0;
-        rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, a.stream);
+        rc = t3::bin_poses<T, N_IN>(a.rotation, a.translation, grid, a.P, b0, nb, ws, pl, cache, a.stream);
         if (rc != DPR_OK) return rc;
         rc = use_tma ? launch(t3::pullback_tile3d_kernel<T, N_IN, true>, b0, nb) : launch(t3::pullback_tile3d_kernel<T, N_IN, false>, b0, nb);
         if (rc != DPR_OK) return rc;
@@ -579,9 +583,12 @@ template <typename T>
 int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     if (a.n_out == 3 && a.n_in == 3 && tuning().pullback_algo != 1 && a.P > 0 && a.B > 0 &&
         (tuning().pullback_algo == 7 || (tuning().pullback_algo == 0 && t3::worthwhile(a.grid, a.P, a.B)))) {
-        const t3::Plan pl = t3::make_plan(a.n_in, a.grid, a.P, a.B, (int)sizeof(T), true);
+        const t3::Plan pl = t3::make_plan(a.n_in, a.grid, a.P, a.B, (int)sizeof(T));
         if (pl.ok && a.workspace && a.workspace_bytes >= pl.total) return pullback_tile3d<T, 3>(a, dev, pl);
     }
+    // every other path may overwrite a workspace that holds cached bins of the 3-d tile path: un-mark them first
+    if (tuning().binning_cache == 1 && a.workspace && a.workspace_bytes >= 256)
+        DPR_CUDA_TRY(cudaMemsetAsync(static_cast<char*>(a.workspace) + t3::cache_valid_offset(), 0, sizeof(unsigned long long), a.stream));
     if constexpr (sizeof(T) == 4) {
         // TMA-staged kernel: whole pose image on chip, 16-byte aligned images, enough points to fill the CTAs
         const int64_t cells2 = a.n_out == 2 ? a.grid[0] * a.grid[1] : 0;
@@ -618,7 +625,7 @@ size_t pullback_workspace_bytes(int n_in, int n_out, const int64_t* grid, int64_
     const size_t sorted = make_sort_plan(n_in, P, sizeof_T, true, 256).total;
     size_t need = sorted;
     if (n_out == 3 && n_in == 3 && grid) {     // tile-binned 3-d path
-        const t3::Plan pl = t3::make_plan(n_in, grid, P, B, sizeof_T, true);
+        const t3::Plan pl = t3::make_plan(n_in, grid, P, B, sizeof_T);
         if (pl.ok && (tuning().pullback_algo == 7 || t3::worthwhile(grid, P, B)) && pl.total > need) need = pl.total;
     }
     return need;

@@ -26,6 +26,7 @@
 #pragma once
 #include <cuda.h>
 
+#include <cstddef>
 #include <type_traits>
 
 #include "dpr_common.cuh"
@@ -45,6 +46,100 @@ struct alignas(4 * sizeof(T)) Pt4 { T x, y, z, w; };
 constexpr int kStatMaxBits = 4, kStatBad = 5, kStatSum = 6;     // see "helpers shared by the tile kernels"
 
 // ---------------------------------------------------------------------------------------------------------
+// Binning cache (DPR_OPT_BINNING_CACHE).  The pre-sort and the per-pose bins depend on points, point_weight, rotation and
+// translation only - exactly what a forward call and the pullback that follows it share (the rrule calls raster, then
+// raster_pullback! with the same arguments, ext/DiffPointRasterisationChainRulesCoreExt.jl:56-61).  With the option on, the
+// first 256 bytes of the workspace hold a header with a 128-bit hash of those inputs; every call hashes its inputs on
+// the device (one pass over ~P (N_in + 1) values), and when hash, shapes and the "complete" mark agree, all binning
+// kernels of the call return immediately (the decision is taken on the device: nothing synchronises).  Contract for the
+// caller: zero the first 256 bytes of a workspace when it is allocated, and leave the workspace alone between calls.
+// Every library path that writes into a workspace without going through the cache clears the mark first.
+// ---------------------------------------------------------------------------------------------------------
+struct CacheHeader {
+    unsigned long long magic, hash[2], params, valid;      // persistent between calls
+    unsigned long long acc[2];                              // this call's hash accumulators (zeroed by the host)
+    unsigned int done_blocks, skip;                         // scratch; skip = 1: the cached bins are valid for this call
+};
+constexpr unsigned long long kCacheMagic = 0x4450523354494c45ull;   // "DPR3TILE"
+
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {      // splitmix64 finaliser
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+template <typename T>
+__device__ __forceinline__ unsigned long long raw_bits(T v) {
+    if constexpr (sizeof(T) == 4) return (unsigned long long)__float_as_uint((float)v);
+    else return (unsigned long long)__double_as_longlong((double)v);
+}
+template <typename T>
+__global__ void __launch_bounds__(256) hash_inputs_kernel(const T* __restrict__ points, int64_t n_pts, const T* __restrict__ pw, int64_t n_pw,
+                                                          const T* __restrict__ rot, int64_t n_rot, const T* __restrict__ tr, int64_t n_tr,
+                                                          unsigned long long params, CacheHeader* __restrict__ h) {
+    unsigned long long h1 = 0, h2 = 0;
+    const int64_t n = n_pts + n_pw + n_rot + n_tr;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    constexpr int U = 4;                    // independent loads in flight per thread
+    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
+        T v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            v[u] = T(0);
+            if (i < n_pts) v[u] = __ldg(points + i);
+            else if (i < n_pts + n_pw) v[u] = __ldg(pw + (i - n_pts));
+            else if (i < n_pts + n_pw + n_rot) v[u] = __ldg(rot + (i - n_pts - n_pw));
+            else if (i < n) v[u] = __ldg(tr + (i - n_pts - n_pw - n_rot));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t i = i0 + u * stride;
+            if (i >= n) continue;
+            // position-dependent terms, summed: independent of the order of the threads, dependent on the order of the data
+            const unsigned long long t = mix64(raw_bits(v[u]) + (unsigned long long)(i + 1) * 0x9e3779b97f4a7c15ull);
+            h1 += t;
+            h2 += mix64(t ^ 0xd6e8feb86659fd93ull);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        h1 += __shfl_xor_sync(0xffffffffu, h1, o);
+        h2 += __shfl_xor_sync(0xffffffffu, h2, o);
+    }
+    __shared__ unsigned long long s1[8], s2[8];
+    __shared__ bool last;
+    if ((threadIdx.x & 31) == 0) { s1[threadIdx.x >> 5] = h1; s2[threadIdx.x >> 5] = h2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w) { h1 += s1[w]; h2 += s2[w]; }
+        atomicAdd(&h->acc[0], h1);
+        atomicAdd(&h->acc[1], h2);
+        __threadfence();
+        last = atomicAdd(&h->done_blocks, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            const unsigned long long a0 = *reinterpret_cast<volatile unsigned long long*>(&h->acc[0]);
+            const unsigned long long a1 = *reinterpret_cast<volatile unsigned long long*>(&h->acc[1]);
+            const bool hit = h->magic == kCacheMagic && h->valid == 1ull && h->params == params && h->hash[0] == a0 && h->hash[1] == a1;
+            if (!hit) {
+                h->magic = kCacheMagic;
+                h->hash[0] = a0;
+                h->hash[1] = a1;
+                h->params = params;
+                h->valid = 0ull;        // set by the tile kernel that runs after the binning kernels of this call
+            }
+            h->skip = hit ? 1u : 0u;
+        }
+    }
+}
+// zeroes [ptr, ptr + n16 * 16) unless the cache hit
+static __global__ void __launch_bounds__(256) clear_unless_cached_kernel(uint4* __restrict__ ptr, int64_t n16, const unsigned int* __restrict__ skip) {
+    if (skip && *skip) return;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) ptr[i] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // exclusive scan of n 32-bit counters in place, one pass (decoupled look-back, Merrill & Garland 2016): CTAs take their
 // chunk from a ticket counter, publish {flag, value} in one 64-bit word and resolve their prefix with a warp-wide
 // look-back.  `state` (one word per chunk) and `ticket` must be zero on entry.
@@ -55,8 +150,9 @@ constexpr int kScanChunk = 4096;
 
 static __global__ void __launch_bounds__(1024) scan_lookback_kernel(uint32_t* __restrict__ data, int64_t n,
                                                                     unsigned long long* __restrict__ state,
-                                                                    uint32_t* __restrict__ ticket) {
+                                                                    uint32_t* __restrict__ ticket, const unsigned int* __restrict__ skip) {
     __shared__ uint32_t s_chunk, s_base, warp_tot[32];
+    if (skip && *skip) return;                 // binning cache hit (uniform)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) s_chunk = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -156,11 +252,11 @@ static int clear_scan_region(char* ws, const ScanRegion& r, cudaStream_t stream)
     return DPR_OK;
 }
 // after the data was cleared by clear_scan_region and filled by a counting kernel
-static int launch_scan(char* ws, const ScanRegion& r, cudaStream_t stream, const char* name) {
+static int launch_scan(char* ws, const ScanRegion& r, cudaStream_t stream, const char* name, const unsigned int* skip = nullptr) {
     LaunchScope scope(name, stream);
     scan_lookback_kernel<<<(unsigned)r.chunks, 1024, 0, stream>>>(reinterpret_cast<uint32_t*>(ws + r.off_data), r.n,
                                                                   reinterpret_cast<unsigned long long*>(ws + r.off_state),
-                                                                  reinterpret_cast<uint32_t*>(ws + r.off_ticket));
+                                                                  reinterpret_cast<uint32_t*>(ws + r.off_ticket), skip);
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
 }
@@ -169,11 +265,23 @@ static int launch_scan(char* ws, const ScanRegion& r, cudaStream_t stream, const
 // 1. pre-sort: keys + histogram come from bin_count_kernel (dpr_sort.cuh); this scatter writes the packed copy
 // ---------------------------------------------------------------------------------------------------------
 template <typename T, int N_IN>
+__global__ void __launch_bounds__(256) sort_count_kernel(const T* __restrict__ points, int64_t P, int bits, uint32_t* __restrict__ keys,
+                                                         uint32_t* __restrict__ counts, const unsigned int* __restrict__ skip) {
+    if (skip && *skip) return;                 // binning cache hit (uniform)
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
+        const uint32_t k = morton_key<T, N_IN>(points, p, bits);
+        keys[p] = k;
+        atomicAdd(counts + k, 1u);
+    }
+}
+template <typename T, int N_IN>
 __global__ void __launch_bounds__(256) sort_scatter4_kernel(const T* __restrict__ points, const T* __restrict__ point_weight,
                                                             int64_t P, const uint32_t* __restrict__ keys,
                                                             uint32_t* __restrict__ offsets, int32_t* __restrict__ perm,
-                                                            Pt4<T>* __restrict__ pts4, Pt4<T>* __restrict__ acc4,
-                                                            uint32_t* __restrict__ stats) {
+                                                            Pt4<T>* __restrict__ pts4, uint32_t* __restrict__ stats,
+                                                            const unsigned int* __restrict__ skip) {
+    if (skip && *skip) return;                 // binning cache hit (uniform)
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     float wmax = 0.f, wsum = 0.f;
     bool bad = false;
@@ -186,7 +294,6 @@ __global__ void __launch_bounds__(256) sort_scatter4_kernel(const T* __restrict_
         q.w = point_weight ? __ldg(point_weight + p) : T(1);
         pts4[pos] = q;
         perm[pos] = (int32_t)p;
-        if (acc4) { Pt4<T> z; z.x = z.y = z.z = z.w = T(0); acc4[pos] = z; }
         const float w = (float)q.w;
         bad = bad || !(w >= 0.f) || !(w < 3e38f);     // negative, NaN or infinite weights: no fixed-point accumulation
         wmax = fmaxf(wmax, w);
@@ -244,7 +351,9 @@ __device__ __forceinline__ uint32_t tile_key(const int (&i0)[3], const int (&g)[
 template <typename T, int N_IN>
 __global__ void __launch_bounds__(256) tile_count_kernel(const Pt4<T>* __restrict__ pts4, int P, const T* __restrict__ rotation,
                                                          const T* __restrict__ translation, Grid<T, 3> grid, TileGeom tg,
-                                                         uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys, int64_t b0) {
+                                                         uint32_t* __restrict__ cnt, uint32_t* __restrict__ keys, int64_t b0,
+                                                         const unsigned int* __restrict__ skip) {
+    if (skip && *skip) return;                 // binning cache hit (uniform)
     constexpr int K = 4;
     const int bl = blockIdx.y;
     Pose<T, N_IN, 3> pose;
@@ -271,7 +380,8 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const Pt4<T>* __restric
 }
 // pass 2 (after the scan): the sorted point index of every pair goes to its list; no transform, the keys are re-read
 static __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ keys,
-                                                                  uint32_t* __restrict__ entries) {
+                                                                  uint32_t* __restrict__ entries, const unsigned int* __restrict__ skip) {
+    if (skip && *skip) return;                 // binning cache hit (uniform)
     constexpr int K = 4;
     const uint32_t* __restrict__ my_keys = keys + (size_t)blockIdx.y * (size_t)P;
     const int lane = threadIdx.x & 31;
@@ -432,9 +542,11 @@ __global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
 fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt,
                   const T* __restrict__ rotation, const T* __restrict__ translation, const T* __restrict__ background,
                   const T* __restrict__ out_weight, T* __restrict__ out, Grid<T, 3> grid, TileGeom tg, int64_t b0,
-                  const uint32_t* __restrict__ pw_stats, int64_t P, int fixed_bits) {
+                  const uint32_t* __restrict__ pw_stats, int64_t P, int fixed_bits, unsigned long long* __restrict__ cache_valid) {
     using CM = CellMap<T>;
     using FT = FwdTile<T>;
+    // this kernel runs after the binning kernels of the call: the cached bins are complete (see CacheHeader)
+    if (cache_valid && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *cache_valid = 1ull;
     constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -702,9 +814,11 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
                        const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt, const T* __restrict__ rotation,
                        const T* __restrict__ translation, const T* __restrict__ out_weight, Pt4<T>* __restrict__ acc4,
                        T* __restrict__ d_rotation, T* __restrict__ d_translation, T* __restrict__ d_background,
-                       T* __restrict__ d_out_weight, Grid<T, 3> grid, TileGeom tg, int64_t b0) {
+                       T* __restrict__ d_out_weight, Grid<T, 3> grid, TileGeom tg, int64_t b0,
+                       unsigned long long* __restrict__ cache_valid) {
     constexpr int NR = 3 * N_IN, NV = NR + 3 + 1;     // d_rotation (col-major 3 x N_IN), d_translation, d_out_weight
     using CM = CellMap<T>;
+    if (cache_valid && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *cache_valid = 1ull;
     constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -921,7 +1035,9 @@ struct Plan {
     size_t off_keys = 0, off_perm = 0, off_pts4 = 0, off_acc4 = 0, off_entries = 0, off_tile_keys = 0, total = 0;
 };
 
-inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int sizeof_T, bool pullback) {
+// (the layout is the same for the forward and the pullback - the accumulator of the pullback is always reserved - so that
+// both can share one workspace and the binning cache)
+inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int sizeof_T) {
     Plan pl;
     if (n_in > 3 || P < 1 || B < 1 || P >= ((int64_t)1 << 30)) return pl;
     const int TS[3] = {TX, TY, TZ};
@@ -953,7 +1069,7 @@ inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int s
     pl.off_keys = o;    o = al(o + sizeof(uint32_t) * (size_t)P);
     pl.off_perm = o;    o = al(o + sizeof(int32_t) * (size_t)P);
     pl.off_pts4 = o;    o = al(o + (size_t)sizeof_T * 4 * (size_t)P);
-    pl.off_acc4 = o;    o = al(o + (pullback ? (size_t)sizeof_T * 4 * (size_t)P : 0));
+    pl.off_acc4 = o;    o = al(o + (size_t)sizeof_T * 4 * (size_t)P);
     pl.sort_scan = make_scan_region(o, (int64_t)1 << (bits * n_in));
     o = pl.sort_scan.off_ticket + pl.sort_scan.bytes;
     pl.tile_scan = make_scan_region(o, group * n_tiles * 8);
@@ -965,27 +1081,75 @@ inline Plan make_plan(int n_in, const int64_t* grid, int64_t P, int64_t B, int s
     return pl;
 }
 
+// per-call state of the binning cache
+struct CacheCtl {
+    bool enabled = false;
+    const unsigned int* skip = nullptr;          // device flag: 1 = the cached bins are valid, binning kernels return
+    unsigned long long* valid = nullptr;         // device word the tile kernel sets once the bins are complete
+};
+inline size_t cache_valid_offset() { return offsetof(CacheHeader, valid); }
+
+// Hashes the inputs and decides (on the device) whether the bins in the workspace can be reused.
+template <typename T>
+static int cache_begin(CacheCtl& ctl, char* ws, const Plan& pl, int n_in, const int64_t* grid, const T* points, const T* point_weight,
+                       const T* rotation, const T* translation, int64_t P, int64_t B, const DeviceInfo& dev, cudaStream_t stream) {
+    ctl = CacheCtl{};
+    if (tuning().binning_cache != 1) return DPR_OK;
+    CacheHeader* h = reinterpret_cast<CacheHeader*>(ws);
+    if (pl.group != B) {            // several passes share the entry buffer: nothing to keep; un-mark whatever is there
+        DPR_CUDA_TRY(cudaMemsetAsync(ws + cache_valid_offset(), 0, sizeof(unsigned long long), stream));
+        return DPR_OK;
+    }
+    DPR_CUDA_TRY(cudaMemsetAsync(&h->acc[0], 0, sizeof(CacheHeader) - offsetof(CacheHeader, acc), stream));
+    unsigned long long params = 0x9e3779b97f4a7c15ull;
+    auto fold = [&](unsigned long long v) { params = (params ^ v) * 0xff51afd7ed558ccdull; params ^= params >> 29; };
+    fold((unsigned long long)P); fold((unsigned long long)B); fold((unsigned long long)n_in); fold(sizeof(T));
+    fold((unsigned long long)grid[0]); fold((unsigned long long)grid[1]); fold((unsigned long long)grid[2]);
+    fold(point_weight ? 1ull : 0ull); fold((unsigned long long)pl.total);
+    const int64_t n = P * n_in + (point_weight ? P : 0) + B * 3 * n_in + B * 3;
+    int64_t blocks = (n + 256 * 4 - 1) / (256 * 4);
+    if (blocks > (int64_t)dev.sm_count * 32) blocks = (int64_t)dev.sm_count * 32;
+    if (blocks < 1) blocks = 1;
+    {
+        LaunchScope scope("tile3_cache_hash", stream);
+        hash_inputs_kernel<T><<<(unsigned)blocks, 256, 0, stream>>>(points, P * n_in, point_weight, point_weight ? P : 0, rotation, B * 3 * n_in,
+                                                                    translation, B * 3, params, h);
+    }
+    DPR_CUDA_TRY(cudaGetLastError());
+    ctl.enabled = true;
+    ctl.skip = &h->skip;
+    ctl.valid = &h->valid;
+    return DPR_OK;
+}
+
 template <typename T, int N_IN>
-static int presort(const T* points, const T* point_weight, int64_t P, char* ws, const Plan& pl, bool zero_acc,
+static int presort(const T* points, const T* point_weight, int64_t P, char* ws, const Plan& pl, const CacheCtl& ctl,
                    const DeviceInfo& dev, cudaStream_t stream) {
     uint32_t* keys = reinterpret_cast<uint32_t*>(ws + pl.off_keys);
     uint32_t* counts = reinterpret_cast<uint32_t*>(ws + pl.sort_scan.off_data);
-    int rc = clear_scan_region(ws, pl.sort_scan, stream);
-    if (rc != DPR_OK) return rc;
+    int rc;
+    if (ctl.enabled) {
+        // both scan regions (adjacent) in one conditional pass: a cache hit must keep the counters and the statistics
+        const size_t lo = pl.sort_scan.off_ticket, hi = pl.tile_scan.off_ticket + pl.tile_scan.bytes;
+        LaunchScope scope("tile3_clear", stream);
+        clear_unless_cached_kernel<<<(unsigned)dev.sm_count * 4, 256, 0, stream>>>(reinterpret_cast<uint4*>(ws + lo), (int64_t)((hi - lo) / 16), ctl.skip);
+    } else {
+        rc = clear_scan_region(ws, pl.sort_scan, stream);
+        if (rc != DPR_OK) return rc;
+    }
     int64_t blocks = (P + 255) / 256;
     if (blocks > (int64_t)dev.sm_count * 16) blocks = (int64_t)dev.sm_count * 16;
     {
         LaunchScope scope("tile3_sort_count", stream);
-        bin_count_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(points, P, pl.sort_bits, keys, counts);
+        sort_count_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(points, P, pl.sort_bits, keys, counts, ctl.skip);
     }
-    rc = launch_scan(ws, pl.sort_scan, stream, "tile3_sort_scan");
+    rc = launch_scan(ws, pl.sort_scan, stream, "tile3_sort_scan", ctl.skip);
     if (rc != DPR_OK) return rc;
     {
         LaunchScope scope("tile3_sort_scatter", stream);
         sort_scatter4_kernel<T, N_IN><<<(unsigned)blocks, 256, 0, stream>>>(
             points, point_weight, P, keys, counts, reinterpret_cast<int32_t*>(ws + pl.off_perm),
-            reinterpret_cast<Pt4<T>*>(ws + pl.off_pts4), zero_acc ? reinterpret_cast<Pt4<T>*>(ws + pl.off_acc4) : nullptr,
-            reinterpret_cast<uint32_t*>(ws + pl.sort_scan.off_ticket));
+            reinterpret_cast<Pt4<T>*>(ws + pl.off_pts4), reinterpret_cast<uint32_t*>(ws + pl.sort_scan.off_ticket), ctl.skip);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
@@ -994,12 +1158,15 @@ static int presort(const T* points, const T* point_weight, int64_t P, char* ws, 
 // count + scan + scatter for poses [b0, b0 + nb)
 template <typename T, int N_IN>
 static int bin_poses(const T* rotation, const T* translation, const Grid<T, 3>& grid, int64_t P, int64_t b0, int64_t nb,
-                     char* ws, const Plan& pl, cudaStream_t stream) {
+                     char* ws, const Plan& pl, const CacheCtl& ctl, cudaStream_t stream) {
     ScanRegion sr = pl.tile_scan;
     sr.n = nb * pl.tg.n_tiles * 8;
     sr.chunks = (int)((sr.n + kScanChunk - 1) / kScanChunk);
-    int rc = clear_scan_region(ws, sr, stream);
-    if (rc != DPR_OK) return rc;
+    int rc;
+    if (!ctl.enabled) {             // (with the cache the region was cleared, conditionally, together with the pre-sort's)
+        rc = clear_scan_region(ws, sr, stream);
+        if (rc != DPR_OK) return rc;
+    }
     const Pt4<T>* pts4 = reinterpret_cast<const Pt4<T>*>(ws + pl.off_pts4);
     uint32_t* cnt = reinterpret_cast<uint32_t*>(ws + sr.off_data);
     uint32_t* entries = reinterpret_cast<uint32_t*>(ws + pl.off_entries);
@@ -1007,13 +1174,13 @@ static int bin_poses(const T* rotation, const T* translation, const Grid<T, 3>& 
     const dim3 gridDim3((unsigned)((P + 1023) / 1024), (unsigned)nb);
     {
         LaunchScope scope("tile3_bin_count", stream);
-        tile_count_kernel<T, N_IN><<<gridDim3, 256, 0, stream>>>(pts4, (int)P, rotation, translation, grid, pl.tg, cnt, tile_keys, b0);
+        tile_count_kernel<T, N_IN><<<gridDim3, 256, 0, stream>>>(pts4, (int)P, rotation, translation, grid, pl.tg, cnt, tile_keys, b0, ctl.skip);
     }
-    rc = launch_scan(ws, sr, stream, "tile3_bin_scan");
+    rc = launch_scan(ws, sr, stream, "tile3_bin_scan", ctl.skip);
     if (rc != DPR_OK) return rc;
     {
         LaunchScope scope("tile3_bin_scatter", stream);
-        tile_scatter_kernel<<<gridDim3, 256, 0, stream>>>((int)P, cnt, tile_keys, entries);
+        tile_scatter_kernel<<<gridDim3, 256, 0, stream>>>((int)P, cnt, tile_keys, entries, ctl.skip);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;

@@ -110,16 +110,19 @@ _workspaces = {}
 
 
 def _workspace(op: int, n_in, n_out, grid, P, B, dtype, device):
-    """Scratch buffer of dpr_workspace_bytes() for one call (cached per device and stream; the glue owns it, like the
-    CuVector{UInt8} a Julia caller would allocate)."""
+    """Scratch buffer of dpr_workspace_bytes() for one call, cached per device and stream and SHARED by raster and
+    raster_pullback! (the glue owns it, like the CuVector{UInt8} a Julia caller would allocate): with
+    DPR_OPT_BINNING_CACHE the pullback that follows a forward on the same inputs - the rrule - reuses the point bins the
+    forward left there.  The first 256 bytes are zeroed on allocation, as that option's contract asks."""
     lib = _lib.load()
     need = int(lib.dpr_workspace_bytes(op, n_in, n_out, grid, P, B, 4 if dtype == torch.float32 else 8))
     if need == 0:
         return None, 0
-    key = (device, torch.cuda.current_stream(device).cuda_stream, op)
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
     buf = _workspaces.get(key)
     if buf is None or buf.numel() < need:
         buf = torch.empty(max(need, 4096), dtype=torch.uint8, device=device)
+        buf[:256].zero_()
         _workspaces[key] = buf
     return buf, buf.numel()
 

@@ -32,22 +32,46 @@ function _check(rc::Cint)
     return error("libdpr: $msg" * (isempty(detail) ? "" : " [$detail]"))
 end
 
-# FillArrays defaults (src/interface.jl:368-394) map to NULL: Zeros background, Ones weights.
-# Any other Fill value is materialised (rare; keeps the semantics of the reference).
+# FillArrays defaults (src/interface.jl:368-394) map to NULL - but only the default of THAT argument: the C ABI reads
+# NULL as background = 0 and as weight = 1, so `background = Ones(..)` or `out_weight = Zeros(..)` must not become NULL.
+# Every other Fill value is materialised on the device (rare; keeps the semantics of the reference, which honours the
+# actual Fill value: ext/DiffPointRasterisationCUDAExt.jl:15-17).
 _null(::Type{T}) where {T} = reinterpret(CuPtr{T}, CUDA.CU_NULL)
-_devptr(::Type{T}, a::CuArray{T}) where {T} = pointer(a)
-_devptr(::Type{T}, a::FillArrays.Zeros{T}) where {T} = _null(T)
-_devptr(::Type{T}, a::FillArrays.Ones{T}) where {T} = _null(T)
-_materialise(a::CuArray) = a
-_materialise(a::FillArrays.Zeros) = a
-_materialise(a::FillArrays.Ones) = a
-_materialise(a::FillArrays.AbstractFill{T}) where {T} = CUDA.fill(FillArrays.getindex_value(a), size(a)...)
+_fill_on_device(a::FillArrays.AbstractFill{T}) where {T} = CUDA.fill(T(FillArrays.getindex_value(a)), size(a)...)
+# background: Zeros -> NULL
+_bg(a::CuArray) = a
+_bg(a::FillArrays.Zeros) = a
+_bg(a::FillArrays.AbstractFill) = _fill_on_device(a)
+_bgptr(::Type{T}, a::CuArray{T}) where {T} = pointer(a)
+_bgptr(::Type{T}, a::FillArrays.Zeros{T}) where {T} = _null(T)
+# out_weight / point_weight: Ones -> NULL
+_wt(a::CuArray) = a
+_wt(a::FillArrays.Ones) = a
+_wt(a::FillArrays.AbstractFill) = _fill_on_device(a)
+_wptr(::Type{T}, a::CuArray{T}) where {T} = pointer(a)
+_wptr(::Type{T}, a::FillArrays.Ones{T}) where {T} = _null(T)
 
+# One scratch buffer per task, shared by raster! and raster_pullback! and kept between calls: with DPR_OPT_BINNING_CACHE
+# (option 8) the pullback that follows a forward on the same inputs - the rrule's call order - reuses the point bins the
+# forward left in it.  The option's contract: the first 256 bytes are zero when the buffer is allocated (CUDA.zeros),
+# and nobody else writes into it.
+const _BINNING_CACHE_ON = Ref(false)
 function _workspace(op, n_in, n_out, grid::Vector{Int64}, P, B, ::Type{T}) where {T}
+    if !_BINNING_CACHE_ON[]
+        ccall((:dpr_set_option, libdpr), Cint, (Cint, Int64), 8, 1)
+        _BINNING_CACHE_ON[] = true
+    end
     nbytes = ccall((:dpr_workspace_bytes, libdpr), Csize_t,
                    (Cint, Cint, Cint, Ptr{Int64}, Int64, Int64, Cint),
                    op, n_in, n_out, grid, P, B, sizeof(T))
-    return CuVector{UInt8}(undef, max(Int(nbytes), 256))
+    need = max(Int(nbytes), 256)
+    tls = task_local_storage()
+    ws = get(tls, :dpr_b200_workspace, nothing)
+    if ws === nothing || length(ws) < need || CUDA.device(ws) != CUDA.device()
+        ws = CUDA.zeros(UInt8, need)
+        tls[:dpr_b200_workspace] = ws
+    end
+    return ws::CuVector{UInt8}
 end
 
 # --------------------------------------------------------------------------------------------------------------
@@ -69,7 +93,7 @@ function DiffPointRasterisation.raster!(
     n_points = length(points)
     @argcheck length(point_weight) == n_points
 
-    background, out_weight, point_weight = _materialise(background), _materialise(out_weight), _materialise(point_weight)
+    background, out_weight, point_weight = _bg(background), _wt(out_weight), _wt(point_weight)
     grid = collect(Int64, size(out)[1:N_out])
     ws = _workspace(DPR_OP_FORWARD, N_in, N_out, grid, n_points, batch_size, T)
     GC.@preserve out points rotation translation background out_weight point_weight ws begin
@@ -79,8 +103,8 @@ function DiffPointRasterisation.raster!(
                    CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                   N_in, N_out, grid, n_points, batch_size,
                   reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
-                  reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, background), _devptr(T, out_weight),
-                  _devptr(T, point_weight), pointer(out), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
+                  reinterpret(CuPtr{T}, pointer(translation)), _bgptr(T, background), _wptr(T, out_weight),
+                  _wptr(T, point_weight), pointer(out), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
                   CUDA.stream().handle)
         else
             ccall((:dpr_raster_forward_f64, libdpr), Cint,
@@ -88,8 +112,8 @@ function DiffPointRasterisation.raster!(
                    CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                   N_in, N_out, grid, n_points, batch_size,
                   reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
-                  reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, background), _devptr(T, out_weight),
-                  _devptr(T, point_weight), pointer(out), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
+                  reinterpret(CuPtr{T}, pointer(translation)), _bgptr(T, background), _wptr(T, out_weight),
+                  _wptr(T, point_weight), pointer(out), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
                   CUDA.stream().handle)
         end
         _check(rc)
@@ -168,7 +192,7 @@ function DiffPointRasterisation.raster_pullback!(
     @argcheck size(ds_dpoints) == (N_in, n_points)
     batch_size = length(batch_axis)
 
-    out_weight, point_weight = _materialise(out_weight), _materialise(point_weight)
+    out_weight, point_weight = _wt(out_weight), _wt(point_weight)
     grid = collect(Int64, size(ds_dout)[1:N_out])
     ws = _workspace(DPR_OP_PULLBACK, N_in, N_out, grid, n_points, batch_size, T)
     # `ccall` needs its argument types as a literal tuple and takes no splatted arguments, so both element types are
@@ -180,7 +204,7 @@ function DiffPointRasterisation.raster_pullback!(
                    CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                   N_in, N_out, grid, n_points, batch_size, pointer(ds_dout),
                   reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
-                  reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, out_weight), _devptr(T, point_weight),
+                  reinterpret(CuPtr{T}, pointer(translation)), _wptr(T, out_weight), _wptr(T, point_weight),
                   pointer(ds_dpoints), pointer(ds_drotation), pointer(ds_dtranslation), pointer(ds_dbackground),
                   pointer(ds_dout_weight), pointer(ds_dpoint_weight), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
                   CUDA.stream().handle)
@@ -190,7 +214,7 @@ function DiffPointRasterisation.raster_pullback!(
                    CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{T}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                   N_in, N_out, grid, n_points, batch_size, pointer(ds_dout),
                   reinterpret(CuPtr{T}, pointer(points)), reinterpret(CuPtr{T}, pointer(rotation)),
-                  reinterpret(CuPtr{T}, pointer(translation)), _devptr(T, out_weight), _devptr(T, point_weight),
+                  reinterpret(CuPtr{T}, pointer(translation)), _wptr(T, out_weight), _wptr(T, point_weight),
                   pointer(ds_dpoints), pointer(ds_drotation), pointer(ds_dtranslation), pointer(ds_dbackground),
                   pointer(ds_dout_weight), pointer(ds_dpoint_weight), reinterpret(CuPtr{Cvoid}, pointer(ws)), sizeof(ws),
                   CUDA.stream().handle)

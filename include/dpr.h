@@ -139,8 +139,14 @@ enum dpr_option {
     DPR_OPT_FORWARD_ACCUM = 5,  /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
     DPR_OPT_POINT_SORT = 6,     /* 0 auto, 1 always sort the points first (pullback: spatially; forward: also by
                                    radius for the one-slab Float32 tile kernel), 2 never                      */
-    DPR_OPT_TILE3D_TMA = 7      /* 3-d tile pullback: 0 auto (tensor-map TMA tile loads, cp.async.bulk.tensor.4d, when rows
+    DPR_OPT_TILE3D_TMA = 7,     /* 3-d tile pullback: 0 auto (tensor-map TMA tile loads, cp.async.bulk.tensor.4d, when rows
                                    are 16-byte multiples), 1 cooperative tile loads only                        */
+    DPR_OPT_BINNING_CACHE = 8   /* 3-d tile path: 1 = the spatial pre-sort and the per-pose bins stay in the caller's workspace
+                                   and are reused by the next call on the same (points, point_weight, rotation,
+                                   translation) - e.g. the pullback after the forward (the rrule,
+                                   ext/DiffPointRasterisationChainRulesCoreExt.jl:56-61).  Validated on the device by a
+                                   128-bit hash of those inputs.  Contract: zero the first 256 bytes of a workspace when
+                                   you allocate it and do not touch it between calls.  0 (default) = off.              */
 };
 int dpr_set_option(int option, int64_t value);
 int64_t dpr_get_option(int option);

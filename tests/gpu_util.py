@@ -33,7 +33,7 @@ class forced:
         self.names = dict(forward_algo=dpr_b200._lib.OPT_FORWARD_ALGO, pullback_algo=dpr_b200._lib.OPT_PULLBACK_ALGO,
                           tile_smem_bytes=dpr_b200._lib.OPT_TILE_SMEM_BYTES, point_split=dpr_b200._lib.OPT_POINT_SPLIT,
                           pose_chunk=dpr_b200._lib.OPT_POSE_CHUNK, forward_accum=dpr_b200._lib.OPT_FORWARD_ACCUM, point_sort=dpr_b200._lib.OPT_POINT_SORT,
-                          tile3d_tma=dpr_b200._lib.OPT_TILE3D_TMA)
+                          tile3d_tma=dpr_b200._lib.OPT_TILE3D_TMA, binning_cache=dpr_b200._lib.OPT_BINNING_CACHE)
 
     def __enter__(self):
         self.old = {k: dpr_b200.get_option(self.names[k]) for k in self.opts}
