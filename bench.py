@@ -379,7 +379,9 @@ def main():
     comm, comm_kind = None, "none"
     if world > 1:
         try:
-            comm, comm_kind = sharded.DprComm(dev), "dpr_comm_allreduce_sum (NCCL via libdpr.so)"
+            comm = sharded.DprComm(dev)
+            comm_kind = ("dpr_comm_allreduce_sum: one-shot peer-memory kernels of libdpr.so (CUDA IPC over NVLink; NCCL only for the bootstrap)"
+                         if comm.uses_peer_memory else "dpr_comm_allreduce_sum (NCCL via libdpr.so)")
         except Exception as e:   # NCCL could not be resolved inside the library: torch.distributed does the all-reduce
             comm, comm_kind = None, f"torch.distributed all_reduce ({type(e).__name__})"
 

@@ -21,10 +21,10 @@ SYMBOLS = [
     "dpr_raster_pullback_host_f64", "dpr_host_alloc", "dpr_host_free", "dpr_host_release",
     "dpr_set_option", "dpr_get_option", "dpr_kernel_launch_count", "dpr_last_path",
     "dpr_profile_enable", "dpr_profile_count", "dpr_profile_get",
-    "dpr_comm_unique_id", "dpr_comm_init_rank", "dpr_comm_destroy", "dpr_comm_allreduce_sum_f32", "dpr_comm_allreduce_sum_f64",
+    "dpr_comm_unique_id", "dpr_comm_init_rank", "dpr_comm_destroy", "dpr_comm_allreduce_sum_f32", "dpr_comm_allreduce_sum_f64", "dpr_comm_uses_peer_memory",
 ]
 
-OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM, OPT_POINT_SORT, OPT_TILE3D_TMA, OPT_BINNING_CACHE = range(9)
+OPT_FORWARD_ALGO, OPT_PULLBACK_ALGO, OPT_TILE_SMEM_BYTES, OPT_POINT_SPLIT, OPT_POSE_CHUNK, OPT_FORWARD_ACCUM, OPT_POINT_SORT, OPT_TILE3D_TMA, OPT_BINNING_CACHE, OPT_COMM_P2P = range(10)
 OP_FORWARD, OP_PULLBACK = 0, 1
 
 _lib = None
@@ -84,6 +84,8 @@ def load() -> ctypes.CDLL:
     lib.dpr_comm_init_rank.argtypes = [ctypes.POINTER(c_p), c_i, c_i, c_p]
     lib.dpr_comm_destroy.restype = c_i
     lib.dpr_comm_destroy.argtypes = [c_p]
+    lib.dpr_comm_uses_peer_memory.restype = c_i
+    lib.dpr_comm_uses_peer_memory.argtypes = [c_p]
     for suf in ("f32", "f64"):
         f = getattr(lib, f"dpr_comm_allreduce_sum_{suf}")
         f.restype = c_i

@@ -571,6 +571,7 @@ int dpr_set_option(int option, int64_t value) {
         case DPR_OPT_POINT_SORT: if (value > 2) return DPR_ERR_BAD_OPTION; g_tuning.point_sort = value; return DPR_OK;
         case DPR_OPT_TILE3D_TMA: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.tile3d_tma = value; return DPR_OK;
         case DPR_OPT_BINNING_CACHE: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.binning_cache = value; return DPR_OK;
+        case DPR_OPT_COMM_P2P: if (value > 1) return DPR_ERR_BAD_OPTION; g_tuning.comm_p2p = value; return DPR_OK;
         default: return DPR_ERR_BAD_OPTION;
     }
 }
@@ -585,6 +586,7 @@ int64_t dpr_get_option(int option) {
         case DPR_OPT_POINT_SORT: return g_tuning.point_sort;
         case DPR_OPT_TILE3D_TMA: return g_tuning.tile3d_tma;
         case DPR_OPT_BINNING_CACHE: return g_tuning.binning_cache;
+        case DPR_OPT_COMM_P2P: return g_tuning.comm_p2p;
         default: return -1;
     }
 }

@@ -27,6 +27,7 @@ struct Tuning {
     std::atomic<int64_t> point_sort{0};      // 0 auto, 1 always sort points spatially, 2 never
     std::atomic<int64_t> forward_accum{0};   // 0 auto (fixed point where eligible), 1 float CAS only
     std::atomic<int64_t> binning_cache{0};   // 3-d tile path: 1 = keep the pre-sort and the bins in the workspace between calls
+    std::atomic<int64_t> comm_p2p{0};        // dpr_comm_*: 0 auto (one-shot peer-memory all-reduce where possible), 1 NCCL only
     std::atomic<int64_t> tile3d_tma{0};      // 3-d tile pullback: 0 auto (tensor-map TMA), 1 cooperative tile loads only
 };
 

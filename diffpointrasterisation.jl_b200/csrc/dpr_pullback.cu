@@ -516,9 +516,13 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     return DPR_OK;
 }
 
-// Float32 images that fit a 2- or 3-stage shared-memory ring: TMA-staged kernel (dpr_pullback_tma.cuh)
+// Float32 images that fit a 2- or 3-stage shared-memory ring: TMA-staged kernel (dpr_pullback_tma.cuh).
+// `padded`: rows are fetched through a tensor map whose box is 4 columns wider than the image (bank-skewed pitch).
+static bool tma2d_can_pad(const int64_t* grid) { return (grid[0] % 4) == 0 && grid[0] + 4 <= 256 && grid[1] <= 256; }
+static int64_t tma2d_stage_words(const int64_t* grid, bool padded) { return (padded ? grid[0] + 4 : grid[0]) * grid[1]; }
+
 template <int N_IN>
-static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, int stages) {
+static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, int stages, bool padded) {
     constexpr int K = 8;
     Grid<float, 2> grid;
     grid.cells = 1;
@@ -526,6 +530,19 @@ static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, i
         grid.g[k] = (int)a.grid[k];
         grid.scale[k] = float(a.grid[k]) / 2.f;
         grid.cells *= a.grid[k];
+    }
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    if (padded) {
+        const cuuint64_t dims[3] = {(cuuint64_t)a.grid[0], (cuuint64_t)a.grid[1], (cuuint64_t)a.B};
+        const cuuint64_t strides[2] = {(cuuint64_t)a.grid[0] * 4, (cuuint64_t)grid.cells * 4};
+        const cuuint32_t box[3] = {(cuuint32_t)(a.grid[0] + 4), (cuuint32_t)a.grid[1], 1u};
+        const cuuint32_t es[3] = {1u, 1u, 1u};
+        EncodeTiledFn enc = tensor_map_encoder();
+        if (!enc || enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.ds_dout), dims, strides, box, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return DPR_ERR_UNSUPPORTED;                 // the caller falls back to the dense 1-d copies
     }
     int rc = zero_gradients(a);
     if (rc != DPR_OK) return rc;
@@ -561,21 +578,26 @@ static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, i
     const int64_t pose_chunk = (a.B + pose_chunks - 1) / pose_chunks;
     pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
     if (point_chunks * pose_chunks > (int64_t)0x7fffffff) return DPR_ERR_BAD_DIMS;
-    const size_t smem = tma_pullback_smem(grid.cells, stages, N_IN);
+    const size_t smem = tma_pullback_smem(tma2d_stage_words(a.grid, padded), stages, N_IN);
     const bool has_pw = a.point_weight != nullptr;
     auto launch = [&](auto kern) -> int {
         { const int rcs = opt_in_smem_once(kern, smem, dev); if (rcs != DPR_OK) return rcs; }
         LaunchScope scope("pullback_tma2d", a.stream);
         kern<<<(unsigned)(point_chunks * pose_chunks), kTmaConsumers + 32, smem, a.stream>>>(
-            a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation, a.d_translation,
+            map, a.ds_dout, pts, a.rotation, a.translation, a.out_weight, pwt, a.d_points, a.d_rotation, a.d_translation,
             a.d_background, a.d_out_weight, a.d_point_weight, perm, grid, (int)a.P, a.B, (int)point_chunks, (int)pose_chunk);
         return DPR_OK;
     };
-    if (stages == 3) rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 3>) : launch(pullback_tma2d_kernel<N_IN, K, false, 3>);
-    else rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 2>) : launch(pullback_tma2d_kernel<N_IN, K, false, 2>);
+    if (padded) {
+        if (stages == 3) rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 3, true>) : launch(pullback_tma2d_kernel<N_IN, K, false, 3, true>);
+        else rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 2, true>) : launch(pullback_tma2d_kernel<N_IN, K, false, 2, true>);
+    } else {
+        if (stages == 3) rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 3, false>) : launch(pullback_tma2d_kernel<N_IN, K, false, 3, false>);
+        else rc = has_pw ? launch(pullback_tma2d_kernel<N_IN, K, true, 2, false>) : launch(pullback_tma2d_kernel<N_IN, K, false, 2, false>);
+    }
     if (rc != DPR_OK) return rc;
     DPR_CUDA_TRY(cudaGetLastError());
-    set_last_path(DPR_OP_PULLBACK, perm ? "tma2d_sorted" : "tma2d");
+    set_last_path(DPR_OP_PULLBACK, padded ? (perm ? "tma2d_padded_sorted" : "tma2d_padded") : (perm ? "tma2d_sorted" : "tma2d"));
     return DPR_OK;
 }
 
@@ -595,13 +617,16 @@ int pullback_dispatch(const PullbackArgs<T>& a, const DeviceInfo& dev) {
         const int64_t algo = tuning().pullback_algo;
         if (a.n_out == 2 && (a.n_in == 2 || a.n_in == 3) && (algo == 0 || algo == 4) && cells2 > 0 && (cells2 % 4) == 0 &&
             (reinterpret_cast<uintptr_t>(a.ds_dout) % 16) == 0 && a.P < (int64_t)0x3fffffff) {
-            int stages = 0;
-            if (tma_pullback_smem(cells2, 3, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 3;
-            else if (tma_pullback_smem(cells2, 2, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 2;
             const bool worth = algo == 4 || (a.P >= 4 * (int64_t)kTmaConsumers * 8 && a.B >= 16);
-            if (stages && worth) {
-                if (a.n_in == 2) return pullback_tma2d<2>(a, dev, stages);
-                if (a.n_in == 3) return pullback_tma2d<3>(a, dev, stages);
+            // padded rows first (tensor-map TMA, bank-skewed pitch), then the dense 1-d copies
+            for (int padded = (tma2d_can_pad(a.grid) && tuning().tile3d_tma != 1) ? 1 : 0; worth && padded >= 0; --padded) {
+                const int64_t words = tma2d_stage_words(a.grid, padded != 0);
+                int stages = 0;
+                if (tma_pullback_smem(words, 3, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 3;
+                else if (tma_pullback_smem(words, 2, a.n_in) <= (size_t)dev.max_smem_optin - 1024) stages = 2;
+                if (!stages) continue;
+                const int rc = a.n_in == 2 ? pullback_tma2d<2>(a, dev, stages, padded != 0) : pullback_tma2d<3>(a, dev, stages, padded != 0);
+                if (rc != DPR_ERR_UNSUPPORTED) return rc;
             }
         }
     }

@@ -9,6 +9,7 @@
 // otherwise idle producer warp sums the staged image: d_background comes from the SAME read of ds_dout
 // (ds_dout crosses HBM once), replacing the separate background_sum pass.
 #pragma once
+#include <cuda.h>
 #include "dpr_common.cuh"
 #include "dpr_pullback_fast.cuh"  // stencil2, butterfly8
 
@@ -21,9 +22,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 
-template <int N_IN, int K, bool HAS_PW, int STAGES>
+// PADDED: the image is fetched with ONE 3-d tensor-map TMA copy (cp.async.bulk.tensor, SASS UTMALDG) whose box is four
+// columns WIDER than the image: the extra columns lie outside the tensor, arrive as zeros, and give the staged image a row
+// pitch of g0 + 4 words.  With the dense pitch (a multiple of the 32 banks) the bank of a cell depends on its column
+// only, and spatially sorted lanes - a blob ~10 pixels wide under every pose - serialised 5.3 ways per LDS (66 % of the
+// kernel's shared-memory wavefronts were bank conflicts, profiles/ncu_full_r01_v10_cfg5_summary.csv); with the padded pitch
+// the bank is (x + 4 y) mod 32.  The consumers' address arithmetic is unchanged apart from the pitch.
+// !PADDED: 1-d bulk copy of the dense image (cp.async.bulk, UBLKCP), for rows that are not multiples of 16 bytes.
+template <int N_IN, int K, bool HAS_PW, int STAGES, bool PADDED>
 __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
-pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict__ points,
+pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __restrict__ ds_dout, const float* __restrict__ points,
                       const float* __restrict__ rotation, const float* __restrict__ translation,
                       const float* __restrict__ out_weight, const float* __restrict__ point_weight,
                       float* __restrict__ d_points, float* __restrict__ d_rotation, float* __restrict__ d_translation,
@@ -32,8 +40,10 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
                       int64_t B, int point_chunks, int pose_chunk) {
     constexpr int NR = 2 * N_IN, NV = NR + 3, PP = (NV + 3) / 4 * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int pitch = PADDED ? grid.g[0] + 4 : grid.g[0];            // words per staged row
     const int cells = (int)grid.cells;
-    const uint32_t img_bytes = (uint32_t)cells * 4u;
+    const int stage_words = pitch * grid.g[1];
+    const uint32_t img_bytes = (uint32_t)stage_words * 4u;           // bytes one copy delivers (zero-filled columns included)
     const size_t stage_stride = ((size_t)img_bytes + 127) / 128 * 128;
     float* tiles = reinterpret_cast<float*>(smem_raw);
     unsigned char* after = smem_raw + stage_stride * STAGES;
@@ -65,8 +75,15 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
         auto issue = [&](int i) {      // lane 0 only
             const int s = i % STAGES;
             mbar_arrive_expect_tx(&full[s], img_bytes);
-            tma_load_1d(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s, ds_dout + (b0 + i) * (int64_t)cells,
-                        img_bytes, &full[s]);
+            if constexpr (PADDED) {
+                asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                                 smem_u32(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s)),
+                             "l"(&map), "r"(0), "r"(0), "r"((int)(b0 + i)), "r"(smem_u32(&full[s]))
+                             : "memory");
+            } else {
+                tma_load_1d(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s, ds_dout + (b0 + i) * (int64_t)cells,
+                            img_bytes, &full[s]);
+            }
         };
         if (lane == 0)
             for (int i = 0; i < STAGES - 1 && i < n_pose; ++i) issue(i);
@@ -81,7 +98,7 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
                 mbar_wait(&full[s], (i / STAGES) & 1);
                 const float4* t4 = reinterpret_cast<const float4*>(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s);
                 float acc0 = 0.f, acc1 = 0.f;
-                for (int q = lane; q < cells / 4; q += 32) {
+                for (int q = lane; q < stage_words / 4; q += 32) {     // (the padding columns are zeros)
                     const float4 v = t4[q];
                     acc0 += v.x + v.y;
                     acc1 += v.z + v.w;
@@ -164,12 +181,12 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
                 const bool valid = (valid_mask >> k) & 1u;
                 const bool x_lo = valid && (unsigned)ix < (unsigned)g[0], x_hi = valid && (unsigned)(ix + 1) < (unsigned)g[0];
                 const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
-                const int off = iy * g[0] + ix;
+                const int off = iy * pitch + ix;
                 float G00 = 0.f, G10 = 0.f, G01 = 0.f, G11 = 0.f;
                 if (x_lo && y_lo) G00 = tile[off];
                 if (x_hi && y_lo) G10 = tile[off + 1];
-                if (x_lo && y_hi) G01 = tile[off + g[0]];
-                if (x_hi && y_hi) G11 = tile[off + g[0] + 1];
+                if (x_lo && y_hi) G01 = tile[off + pitch];
+                if (x_hi && y_hi) G11 = tile[off + pitch + 1];
                 float s_, gx, gy;
                 bilinear_with_gradient(G00, G10, G01, G11, dl[0], dl[1], s_, gx, gy);
                 acc_ow += HAS_PW ? s_ * pw[k] : s_;
@@ -221,6 +238,7 @@ pullback_tma2d_kernel(const float* __restrict__ ds_dout, const float* __restrict
     }
 }
 
+// `cells`: words one stage holds - g0 * g1 (dense) or (g0 + 4) * g1 (padded)
 inline size_t tma_pullback_smem(int64_t cells, int stages, int n_in) {
     const int NV = 2 * n_in + 3, PP = (NV + 3) / 4 * 4;
     const size_t stage_stride = ((size_t)cells * 4 + 127) / 128 * 128;

@@ -58,6 +58,7 @@ class DprComm:
         with torch.cuda.device(device):
             _lib.check(self.lib.dpr_comm_init_rank(ctypes.byref(self.handle), world, rank, raw))
         self.device = device
+        self.uses_peer_memory = bool(self.lib.dpr_comm_uses_peer_memory(self.handle))
 
     def all_reduce_(self, t: torch.Tensor) -> None:
         fn = self.lib.dpr_comm_allreduce_sum_f32 if t.dtype == torch.float32 else self.lib.dpr_comm_allreduce_sum_f64

@@ -124,6 +124,8 @@ int dpr_comm_init_rank(dpr_comm_t* comm, int n_ranks, int rank, const void* id12
 int dpr_comm_destroy(dpr_comm_t comm);
 int dpr_comm_allreduce_sum_f32(dpr_comm_t comm, float* buf, int64_t count, dpr_stream_t stream);
 int dpr_comm_allreduce_sum_f64(dpr_comm_t comm, double* buf, int64_t count, dpr_stream_t stream);
+/* 1 when the communicator serves small payloads with its own peer-memory kernels, 0 when everything goes through NCCL */
+int dpr_comm_uses_peer_memory(dpr_comm_t comm);
 
 /* Introspection / tuning (benchmarks and tests). */
 enum dpr_option {
@@ -139,8 +141,11 @@ enum dpr_option {
     DPR_OPT_FORWARD_ACCUM = 5,  /* forward tile kernel: 0 auto (fixed-point where eligible), 1 float atomics  */
     DPR_OPT_POINT_SORT = 6,     /* 0 auto, 1 always sort the points first (pullback: spatially; forward: also by
                                    radius for the one-slab Float32 tile kernel), 2 never                      */
-    DPR_OPT_TILE3D_TMA = 7,     /* 3-d tile pullback: 0 auto (tensor-map TMA tile loads, cp.async.bulk.tensor.4d, when rows
-                                   are 16-byte multiples), 1 cooperative tile loads only                        */
+    DPR_OPT_TILE3D_TMA = 7,     /* tensor-map TMA (cp.async.bulk.tensor): 0 auto - ds_dout tiles of the 3-d tile pullback and the
+                                   bank-skewed (padded) image copies of the 2-d staged pullback, when rows are 16-byte
+                                   multiples; 1 never (cooperative tile loads / dense 1-d bulk copies)            */
+    DPR_OPT_COMM_P2P = 9,       /* dpr_comm_*: 0 auto (payloads up to 16 MB: one-shot all-reduce over CUDA-IPC mapped peer memory,
+                                   set up by dpr_comm_init_rank), 1 NCCL only.  Set before dpr_comm_init_rank.            */
     DPR_OPT_BINNING_CACHE = 8   /* 3-d tile path: 1 = the spatial pre-sort and the per-pose bins stay in the caller's workspace
                                    and are reused by the next call on the same (points, point_weight, rotation,
                                    translation) - e.g. the pullback after the forward (the rrule,

@@ -30,6 +30,31 @@ t = torch.full((1000,), float(rank + 1), device=dev)
 comm.all_reduce_(t)
 torch.cuda.synchronize()
 assert torch.all(t == sum(range(1, world + 1))), "dpr_comm_allreduce_sum_f32 wrong"
+# the library's all-reduce against torch.distributed's: sizes that are / are not multiples of 16 bytes, both element
+# types, a payload above the peer-memory capacity (NCCL path), and 60 calls back to back (the two symmetric buffers
+# alternate, a rank may be a call ahead of its peers)
+gen = torch.Generator(device=dev).manual_seed(100 + rank)
+for dtype, n in ((torch.float32, 400_003), (torch.float32, 4 * 1_000_000), (torch.float64, 300_001), (torch.float32, 5_000_000)):
+    x = torch.randn(n, generator=gen, device=dev, dtype=dtype)
+    want = x.clone()
+    dist.all_reduce(want)
+    got = x.clone()
+    comm.all_reduce_(got)
+    torch.cuda.synchronize()
+    assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < (1e-6 if dtype == torch.float32 else 1e-14), (dtype, n)
+    ref_bits = got.clone()
+    dist.broadcast(ref_bits, src=0)
+    assert torch.equal(ref_bits, got), "ranks disagree bit-wise"            # same summation order on every rank
+acc = torch.zeros(100_001, device=dev)
+for it in range(60):
+    y = torch.full((100_001,), float(it * world + rank), device=dev)
+    comm.all_reduce_(y)
+    acc += y
+torch.cuda.synchronize()
+want = sum(float(it * world + r) for it in range(60) for r in range(world))
+assert torch.all(acc == want), "back-to-back all-reduces wrong"
+if rank == 0:
+    print("peer-memory all-reduce:", comm.uses_peer_memory)
 for c in (comm, None):
     drv = sharded.PoseShardedRaster(comm=c)
     sh = lambda k: None if full[k] is None else dpr_b200.fortran(sharded.shard_poses(full[k], rank, world))

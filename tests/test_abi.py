@@ -54,9 +54,15 @@ def test_fast_forward_kernel_has_no_packed_fma():
         assert "FFMA2" not in body
         assert "FMUL2" in body and "ATOMS.ADD" in body and "LDG.E.NA." in body
     tma = [c for c in chunks if "pullback_tma2d_kernel" in c.split("\n", 1)[0]]
-    assert len(tma) == 8
-    for body in tma:   # TMA bulk copy + mbarrier pipeline really are in the SASS, and no packed FMA
-        assert "UBLKCP" in body and "SYNCS" in body and "FFMA2" not in body
+    assert len(tma) == 16      # N_in in {2,3} x point weights x stages {2,3} x {dense 1-d copies, padded tensor-map copies}
+    for body in tma:   # TMA copies + mbarrier pipeline really are in the SASS, and no packed FMA
+        assert ("UBLKCP" in body or "UTMALDG" in body) and "SYNCS" in body and "FFMA2" not in body
+    assert sum("UTMALDG.3D" in body for body in tma) == 8 and sum("UBLKCP" in body for body in tma) == 8
+    t3 = [c for c in chunks if "pullback_tile3d_kernel" in c.split("\n", 1)[0]]
+    assert len(t3) == 4        # Float32 / Float64 x {tensor-map TMA tile loads, cooperative loads}
+    assert sum("UTMALDG.4D" in body for body in t3) == 2          # cp.async.bulk.tensor.4d of the ds_dout tiles
+    f3 = [c for c in chunks if "fwd_tile3d_kernelIf" in c.split("\n", 1)[0]]
+    assert len(f3) == 1 and "ATOMS.ADD" in f3[0] and "STG.E" in f3[0]       # native integer shared atomics, 16-byte flush
     pb = [c for c in chunks if "pullback_gather2d_kernelIf" in c.split("\n", 1)[0]]
     assert len(pb) == 8   # N_in in {2,3} x point weights x paired loads
     for body in pb:
@@ -120,3 +126,33 @@ def test_fortran_helpers():
     f = dpr_b200.fortran(c)
     assert dpr_b200.is_fortran(f) and torch.equal(f, c)
     assert np.array_equal(np.asarray(f.permute(2, 1, 0).contiguous()).ravel(), np.asarray(c).ravel(order="F"))
+
+
+def _build_c_abi_smoke():
+    """gcc + the CUDA runtime only: no nvcc, no C++ - what a `ccall` (or cgo / JNI) caller links against."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "c_abi_smoke")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    _lib.load()                                   # builds libdpr.so if it is stale
+    cmd = [shutil.which("gcc") or "gcc", "-O1", "-Wall", "-std=c99", "-I", os.path.join(root, "include"), "-I", os.path.join(cuda, "include"),
+           "-o", exe, os.path.join(root, "tests", "c_abi_smoke.c"), "-L", lib_dir, "-ldpr", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + lib_dir, "-Wl,-rpath," + os.path.join(cuda, "lib64")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+def test_c_abi_smoke_builds_with_plain_c():
+    assert os.path.exists(_build_c_abi_smoke())
+
+
+@pytest.mark.gpu
+def test_c_abi_smoke_runs():
+    """The reference's first known-answer forward (src/raster.jl:143-157) and its pullback from a C program holding raw
+    cudaMalloc pointers - the stand-in for the Julia `ccall` glue."""
+    import subprocess
+    res = subprocess.run([_build_c_abi_smoke()], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and "c_abi_smoke ok" in res.stdout, res.stdout + res.stderr

@@ -27,6 +27,15 @@ def _oracle_pair(d, grid, dtype):
     return out, pb
 
 
+def _faithful_pair(d, grid, dtype):
+    """The reference's own arithmetic: every sum sequential in the element type (src/raster_pullback.jl:57,68-71), thread
+    slabs summed at the end (:115-146)."""
+    args = (d["points"], d["rotation"], d["translation"], d["background"], d["out_weight"], d["point_weight"])
+    out = oracle.raster(grid, *args, dtype=dtype, n_threads=8, f64_accumulate=False)
+    pb = oracle.raster_pullback(d["ds_dout"], *args, dtype=dtype, n_slabs=8, f64_accumulate=False)
+    return out, pb
+
+
 def _check(d, grid, dtype, what=""):
     td = torch.float32 if dtype == np.float32 else torch.float64
     out_ref, pb_ref = _oracle_pair(d, grid, dtype)
@@ -39,6 +48,16 @@ def _check(d, grid, dtype, what=""):
     for k in FIELDS:
         e = rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k))
         assert e <= TOL[dtype], f"{what} pullback.{k} [{dpr_b200.last_path(1)}] rel L2 {e:.3e}"
+    if dtype == np.float32:
+        # north_star's literal wording: "match the reference's own multithreaded CPU implementation ... 1e-5".  That
+        # implementation sums in Float32 and is itself up to a few 1e-5 away from the exact sums (SURVEY.md 7 H5,
+        # profiles/accuracy_r01_v9.txt), so the checkable statement is a triangle bound: the GPU result is no further from
+        # the faithful Float32 path than that path is from the Float64-accumulated one, plus the tolerance.
+        out_f, pb_f = _faithful_pair(d, grid, dtype)
+        assert rel_l2(to_np(out), out_f) <= rel_l2(out_f, out_ref) + 1e-5, f"{what} forward vs faithful Float32"
+        for k in FIELDS:
+            got, f32, acc = to_np(getattr(pb, k)), getattr(pb_f, k), getattr(pb_ref, k)
+            assert rel_l2(got, f32) <= rel_l2(f32, acc) + 1e-5, f"{what} pullback.{k} vs faithful Float32"
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -840,3 +859,72 @@ def test_tile3d_binning_cache():
     with forced(forward_algo=3, pullback_algo=7, binning_cache=0):
         check_out(dpr_b200.raster(grid, *args))
         check_pb(dpr_b200.raster_pullback_(ds, *args))
+
+
+def test_forward_global_grouped_fill():
+    """The global-reduction forward fills and splats the pose images in groups of <= 48 MB once the whole output exceeds
+    96 MB (so a group is still in L2 when its reductions arrive): the grouped branch against a pose subset of the oracle."""
+    grid, B, P = (1024, 1024), 26, 6000          # 26 x 4 MB = 104 MB Float32 -> groups of 12 poses; sparse: stays off the tile path
+    d = make_inputs(321, 3, 2, P, B, grid, np.float32)
+    args = dev_args(d, np.float32)
+    with forced(forward_algo=1):
+        out = dpr_b200.raster(grid, *args)
+        assert dpr_b200.last_path(0).startswith("global_redg")
+    sel = np.array([0, 11, 12, 13, 24, 25])              # both sides of the group boundaries
+    sub = lambda a: None if a is None else np.asfortranarray(a[..., sel])
+    ref = oracle.raster(grid, d["points"], sub(d["rotation"]), sub(d["translation"]), sub(d["background"]), sub(d["out_weight"]),
+                        d["point_weight"], dtype=np.float32, n_threads=6, f64_accumulate=True)
+    assert rel_l2(to_np(out[..., torch.from_numpy(sel).cuda()]), ref) <= 1e-5
+
+
+def test_randomised_3d_shapes_tile_paths():
+    """Random 3-d problems through the tile-binned kernels (forced): odd extents around the 32 x 16 x 16 tile, sliced
+    (element-aligned only) buffers - rows that are not 16-byte multiples take the cooperative tile loads, the others TMA."""
+    rng = np.random.default_rng(777)
+    for trial in range(10):
+        dtype = np.float32 if trial % 2 == 0 else np.float64
+        td = torch.float32 if dtype == np.float32 else torch.float64
+        grid = (int(rng.integers(5, 70)), int(rng.integers(3, 40)), int(rng.integers(3, 40)))
+        if trial % 3 == 0:
+            grid = (grid[0] // 4 * 4 + 4,) + grid[1:]
+        P, B = int(rng.integers(100, 20000)), int(rng.integers(1, 9))
+        d = make_inputs(4000 + trial, 3, 3, P, B, grid, dtype, bool(trial % 2))
+        out_ref, pb_ref = _oracle_pair(d, grid, dtype)
+
+        def sliced(a):
+            if a is None:
+                return None
+            pad = np.zeros(a.shape[:-1] + (3,), dtype=a.dtype)
+            big = to_dev(np.concatenate([pad[..., :1], a, pad[..., :2]], axis=-1), td)
+            return big[..., 1:1 + a.shape[-1]]
+        args = tuple(sliced(d[k]) for k in FIELDS)
+        ds = sliced(d["ds_dout"])
+        big_out = dpr_b200.empty_f(tuple(grid) + (B + 2,), td, "cuda")
+        out = big_out[..., 1:B + 1]
+        with forced(forward_algo=3, pullback_algo=7):
+            dpr_b200.raster_(out, *args)
+            assert dpr_b200.last_path(0).startswith("tile3d")
+            pb = dpr_b200.raster_pullback_(ds, *args)
+            assert dpr_b200.last_path(1).startswith("tile3d")
+        assert rel_l2(to_np(out), out_ref) <= TOL[dtype], (trial, grid, P, B)
+        for k in FIELDS:
+            assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= TOL[dtype], (trial, k, grid, P, B)
+    with forced(forward_algo=3, pullback_algo=7, tile3d_tma=1):          # cooperative loads forced on a TMA-capable shape
+        d = make_inputs(4100, 3, 3, 9000, 3, (32, 16, 16), np.float32)
+        _check(d, (32, 16, 16), np.float32, "tile3d coop")
+        assert dpr_b200.last_path(1) == "tile3d_binned_coop"
+
+
+def test_multi_gpu_check_script():
+    """tests/multi_gpu_check.py under torchrun on two GPUs: the library's NCCL all-reduce and the pose-sharded pullback
+    against a single-GPU run.  Skipped on boxes with one GPU (the driver's -m gpu run); tools/run_r02_multi.sh runs it."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                          "127.0.0.1", "--master-port", "29541", os.path.join(root, "tests", "multi_gpu_check.py")],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0 and "multi_gpu_check ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
