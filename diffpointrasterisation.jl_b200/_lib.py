@@ -19,6 +19,8 @@ SYMBOLS = [
     "dpr_raster_forward_f32", "dpr_raster_forward_f64", "dpr_raster_pullback_f32", "dpr_raster_pullback_f64",
     "dpr_raster_forward_host_f32", "dpr_raster_forward_host_f64", "dpr_raster_pullback_host_f32",
     "dpr_raster_pullback_host_f64", "dpr_host_alloc", "dpr_host_free", "dpr_host_release",
+    "dpr_raster_forward_host_async_f32", "dpr_raster_forward_host_async_f64", "dpr_raster_pullback_host_async_f32",
+    "dpr_raster_pullback_host_async_f64", "dpr_host_wait",
     "dpr_set_option", "dpr_get_option", "dpr_kernel_launch_count", "dpr_last_path",
     "dpr_profile_enable", "dpr_profile_count", "dpr_profile_get",
     "dpr_comm_unique_id", "dpr_comm_init_rank", "dpr_comm_destroy", "dpr_comm_allreduce_sum_f32", "dpr_comm_allreduce_sum_f64", "dpr_comm_uses_peer_memory",
@@ -63,6 +65,14 @@ def load() -> ctypes.CDLL:
         f = getattr(lib, f"dpr_raster_pullback_host_{suf}")
         f.restype = c_i
         f.argtypes = head + [c_p] * 12
+        f = getattr(lib, f"dpr_raster_forward_host_async_{suf}")
+        f.restype = c_i
+        f.argtypes = head + [c_p] * 7 + [ctypes.POINTER(c_p)]
+        f = getattr(lib, f"dpr_raster_pullback_host_async_{suf}")
+        f.restype = c_i
+        f.argtypes = head + [c_p] * 12 + [ctypes.POINTER(c_p)]
+    lib.dpr_host_wait.restype = c_i
+    lib.dpr_host_wait.argtypes = [c_p]
     lib.dpr_host_alloc.restype = c_i
     lib.dpr_host_alloc.argtypes = [ctypes.POINTER(c_p), c_sz]
     lib.dpr_host_free.restype = c_i

@@ -5,6 +5,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <thread>
 #include <utility>
 #include <vector>
 
@@ -189,8 +190,11 @@ struct HostArena {
     void* ws[NSTREAM] = {nullptr, nullptr, nullptr};   // per-stream kernel workspace (dpr_workspace_bytes)
     size_t ws_bytes = 0;
 };
-static std::mutex g_arena_mutex[64];     // one lock per device: a process driving several GPUs from several threads is not serialised
-static HostArena g_arena[64];
+// One arena (and one lock) per device AND operation: a process driving several GPUs from several threads is not serialised,
+// and a forward and a pullback on the same device can run at the same time - their copies then use both directions of the
+// host link (dpr_raster_*_host_async_*).
+static std::mutex g_arena_mutex[64][2];
+static HostArena g_arena[64][2];
 
 static int arena_device(int& dev) {
     dev = -1;
@@ -198,9 +202,9 @@ static int arena_device(int& dev) {
     if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
     return DPR_OK;
 }
-// caller holds g_arena_mutex[dev]
-static int arena_get(int dev, HostArena*& out) {
-    HostArena& a = g_arena[dev];
+// caller holds g_arena_mutex[dev][op]
+static int arena_get(int dev, int op, HostArena*& out) {
+    HostArena& a = g_arena[dev][op];
     if (a.device != dev) {
         // create everything or nothing: a failed call must not leave half an arena behind (the next call would create
         // the streams again and leak the first set)
@@ -256,9 +260,9 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
     int dev_id = -1;
     rc = arena_device(dev_id);
     if (rc != DPR_OK) return rc;
-    std::lock_guard<std::mutex> lock(g_arena_mutex[dev_id]);
+    std::lock_guard<std::mutex> lock(g_arena_mutex[dev_id][DPR_OP_FORWARD]);
     HostArena* ar = nullptr;
-    rc = arena_get(dev_id, ar);
+    rc = arena_get(dev_id, DPR_OP_FORWARD, ar);
     if (rc != DPR_OK) return rc;
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) cells *= grid[k];
@@ -338,9 +342,9 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
     int dev_id = -1;
     rc = arena_device(dev_id);
     if (rc != DPR_OK) return rc;
-    std::lock_guard<std::mutex> lock(g_arena_mutex[dev_id]);
+    std::lock_guard<std::mutex> lock(g_arena_mutex[dev_id][DPR_OP_PULLBACK]);
     HostArena* ar = nullptr;
-    rc = arena_get(dev_id, ar);
+    rc = arena_get(dev_id, DPR_OP_PULLBACK, ar);
     if (rc != DPR_OK) return rc;
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) cells *= grid[k];
@@ -447,6 +451,26 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
 
 using namespace dpr;
 
+// ---- non-blocking host-buffer calls: the blocking entry point runs on a helper thread; dpr_host_wait joins it --------
+struct dpr_ticket {
+    std::thread worker;
+    int rc = DPR_OK;
+    char message[512] = "";
+};
+template <typename Fn>
+static int host_async(dpr_ticket_t* ticket, Fn fn) {
+    if (!ticket) return DPR_ERR_NULL_POINTER;
+    int dev = -1;
+    DPR_CUDA_TRY(cudaGetDevice(&dev));
+    dpr_ticket* t = new dpr_ticket();
+    t->worker = std::thread([t, dev, fn] {
+        cudaSetDevice(dev);                     // the helper thread works on the caller's device
+        t->rc = fn();
+        if (t->rc != DPR_OK) snprintf(t->message, sizeof(t->message), "%s", tl_error);
+    });
+    *ticket = t;
+    return DPR_OK;
+}
 extern "C" {
 
 int dpr_version(void) { return 100; }
@@ -545,18 +569,63 @@ int dpr_host_release(void) {
     int dev = -1;
     DPR_CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) return DPR_ERR_NO_DEVICE;
-    std::lock_guard<std::mutex> lock(g_arena_mutex[dev]);
-    HostArena& a = g_arena[dev];
-    if (a.device != dev) return DPR_OK;
-    for (int i = 0; i < NSTREAM; ++i) { if (a.slot[i]) cudaFree(a.slot[i]); a.slot[i] = nullptr; }
-    a.slot_bytes = 0;
-    for (int i = 0; i < NSTREAM; ++i) { if (a.ws[i]) cudaFree(a.ws[i]); a.ws[i] = nullptr; }
-    a.ws_bytes = 0;
-    for (int i = 0; i < NSTREAM; ++i) { if (cudaMalloc(&a.ws[i], 4096) != cudaSuccess) return DPR_ERR_CUDA; }
-    a.ws_bytes = 4096;
-    if (a.shared) cudaFree(a.shared);
-    a.shared = nullptr; a.shared_bytes = 0;
+    for (int op = 0; op < 2; ++op) {
+        std::lock_guard<std::mutex> lock(g_arena_mutex[dev][op]);
+        HostArena& a = g_arena[dev][op];
+        if (a.device != dev) continue;
+        for (int i = 0; i < NSTREAM; ++i) { if (a.slot[i]) cudaFree(a.slot[i]); a.slot[i] = nullptr; }
+        a.slot_bytes = 0;
+        for (int i = 0; i < NSTREAM; ++i) { if (a.ws[i]) cudaFree(a.ws[i]); a.ws[i] = nullptr; }
+        a.ws_bytes = 0;
+        for (int i = 0; i < NSTREAM; ++i) { if (cudaMalloc(&a.ws[i], 4096) != cudaSuccess) return DPR_ERR_CUDA; }
+        a.ws_bytes = 4096;
+        if (a.shared) cudaFree(a.shared);
+        a.shared = nullptr; a.shared_bytes = 0;
+    }
     return DPR_OK;
+}
+
+int dpr_host_wait(dpr_ticket_t ticket) {
+    if (!ticket) return DPR_ERR_NULL_POINTER;
+    if (ticket->worker.joinable()) ticket->worker.join();
+    const int rc = ticket->rc;
+    if (rc != DPR_OK) set_error_message(ticket->message);
+    delete ticket;
+    return rc;
+}
+int dpr_raster_forward_host_async_f32(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const float* points,
+                                      const float* rotation, const float* translation, const float* background,
+                                      const float* out_weight, const float* point_weight, float* out, dpr_ticket_t* ticket) {
+    if (!grid || n_out < 1 || n_out > kMaxDim) return DPR_ERR_BAD_DIMS;
+    std::vector<int64_t> g(grid, grid + n_out);
+    return host_async(ticket, [=] { return forward_host<float>(n_in, n_out, g.data(), P, B, points, rotation, translation, background, out_weight, point_weight, out); });
+}
+int dpr_raster_forward_host_async_f64(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const double* points,
+                                      const double* rotation, const double* translation, const double* background,
+                                      const double* out_weight, const double* point_weight, double* out, dpr_ticket_t* ticket) {
+    if (!grid || n_out < 1 || n_out > kMaxDim) return DPR_ERR_BAD_DIMS;
+    std::vector<int64_t> g(grid, grid + n_out);
+    return host_async(ticket, [=] { return forward_host<double>(n_in, n_out, g.data(), P, B, points, rotation, translation, background, out_weight, point_weight, out); });
+}
+int dpr_raster_pullback_host_async_f32(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const float* ds_dout,
+                                       const float* points, const float* rotation, const float* translation,
+                                       const float* out_weight, const float* point_weight, float* d_points,
+                                       float* d_rotation, float* d_translation, float* d_background, float* d_out_weight,
+                                       float* d_point_weight, dpr_ticket_t* ticket) {
+    if (!grid || n_out < 1 || n_out > kMaxDim) return DPR_ERR_BAD_DIMS;
+    std::vector<int64_t> g(grid, grid + n_out);
+    return host_async(ticket, [=] { return pullback_host<float>(n_in, n_out, g.data(), P, B, ds_dout, points, rotation, translation, out_weight, point_weight,
+                                                                d_points, d_rotation, d_translation, d_background, d_out_weight, d_point_weight); });
+}
+int dpr_raster_pullback_host_async_f64(int n_in, int n_out, const int64_t* grid, int64_t P, int64_t B, const double* ds_dout,
+                                       const double* points, const double* rotation, const double* translation,
+                                       const double* out_weight, const double* point_weight, double* d_points,
+                                       double* d_rotation, double* d_translation, double* d_background, double* d_out_weight,
+                                       double* d_point_weight, dpr_ticket_t* ticket) {
+    if (!grid || n_out < 1 || n_out > kMaxDim) return DPR_ERR_BAD_DIMS;
+    std::vector<int64_t> g(grid, grid + n_out);
+    return host_async(ticket, [=] { return pullback_host<double>(n_in, n_out, g.data(), P, B, ds_dout, points, rotation, translation, out_weight, point_weight,
+                                                                 d_points, d_rotation, d_translation, d_background, d_out_weight, d_point_weight); });
 }
 
 int dpr_set_option(int option, int64_t value) {

@@ -108,6 +108,31 @@ int dpr_raster_pullback_host_f64(int n_in, int n_out, const int64_t* grid, int64
                                  const double* translation, const double* out_weight, const double* point_weight,
                                  double* d_points, double* d_rotation, double* d_translation, double* d_background,
                                  double* d_out_weight, double* d_point_weight);
+/* Non-blocking variants: the call returns at once with a ticket, the work proceeds on a helper thread (on the device that
+ * was current at the call), dpr_host_wait(ticket) blocks until the results are in the host buffers, returns the status and
+ * frees the ticket.  A forward and a pullback use separate staging arenas, so an INDEPENDENT forward and pullback
+ * (ds_dout not computed from `out`) can overlap: the device -> host copies of `out` and the host -> device copies of
+ * ds_dout then share the link's two directions.  The buffers must stay valid until the wait. */
+typedef struct dpr_ticket* dpr_ticket_t;
+int dpr_raster_forward_host_async_f32(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                      const float* points, const float* rotation, const float* translation,
+                                      const float* background, const float* out_weight, const float* point_weight,
+                                      float* out, dpr_ticket_t* ticket);
+int dpr_raster_forward_host_async_f64(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                      const double* points, const double* rotation, const double* translation,
+                                      const double* background, const double* out_weight, const double* point_weight,
+                                      double* out, dpr_ticket_t* ticket);
+int dpr_raster_pullback_host_async_f32(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                       const float* ds_dout, const float* points, const float* rotation,
+                                       const float* translation, const float* out_weight, const float* point_weight,
+                                       float* d_points, float* d_rotation, float* d_translation, float* d_background,
+                                       float* d_out_weight, float* d_point_weight, dpr_ticket_t* ticket);
+int dpr_raster_pullback_host_async_f64(int n_in, int n_out, const int64_t* grid, int64_t n_points, int64_t batch,
+                                       const double* ds_dout, const double* points, const double* rotation,
+                                       const double* translation, const double* out_weight, const double* point_weight,
+                                       double* d_points, double* d_rotation, double* d_translation, double* d_background,
+                                       double* d_out_weight, double* d_point_weight, dpr_ticket_t* ticket);
+int dpr_host_wait(dpr_ticket_t ticket);
 int dpr_host_alloc(void** ptr, size_t bytes);  /* pinned host memory */
 int dpr_host_free(void* ptr);
 int dpr_host_release(void);                    /* frees the staging arena of the current device */

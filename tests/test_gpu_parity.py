@@ -370,11 +370,13 @@ def test_pullback_tma_staged_images(n_in, weights, B, pose_chunk):
     d["points"][:, :3] = np.array([[5.0, -7.0, 1e30], [0.99, -1.0, 1.0]] + ([[0.0, 0.0, 0.0]] if n_in == 3 else []), dtype=np.float32)
     _, pb_ref = _oracle_pair(d, grid, np.float32)
     for sort in (1, 2):
-        with forced(pullback_algo=4, point_sort=sort, pose_chunk=pose_chunk):
-            pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], torch.float32), *dev_args(d, np.float32))
-            assert dpr_b200.last_path(1) == ("tma2d_sorted" if sort == 1 else "tma2d")
-        for k in FIELDS:
-            assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, (sort, k)
+        for no_tensor_map in (0, 1):       # padded rows through a tensor map (UTMALDG) / dense 1-d bulk copies (UBLKCP)
+            with forced(pullback_algo=4, point_sort=sort, pose_chunk=pose_chunk, tile3d_tma=no_tensor_map):
+                pb = dpr_b200.raster_pullback_(to_dev(d["ds_dout"], torch.float32), *dev_args(d, np.float32))
+                want = "tma2d" + ("" if no_tensor_map else "_padded") + ("_sorted" if sort == 1 else "")
+                assert dpr_b200.last_path(1) == want
+            for k in FIELDS:
+                assert rel_l2(to_np(getattr(pb, k)), getattr(pb_ref, k)) <= 1e-5, (sort, no_tensor_map, k)
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -620,6 +622,26 @@ def test_host_buffer_entry_points(dtype, n_in, n_out, grid, B):
                ptr(g["rotation"]), ptr(g["translation"]), ptr(g["background"]), ptr(g["out_weight"]), ptr(g["point_weight"])))
     for k in FIELDS:
         assert rel_l2(g[k], getattr(pb_ref, k)) <= TOL[dtype], k
+    # the non-blocking variants: forward on a helper thread while the pullback runs on this one (separate arenas)
+    out2 = np.zeros_like(out)
+    g2 = {k: np.zeros_like(v) for k, v in g.items()}
+    ticket = ctypes.c_void_p()
+    _lib.check(getattr(lib, f"dpr_raster_forward_host_async_{suf}")(n_in, n_out, garr, P, B, ptr(h["points"]), ptr(h["rotation"]),
+               ptr(h["translation"]), ptr(h["background"]), ptr(h["out_weight"]), ptr(h["point_weight"]), ptr(out2), ctypes.byref(ticket)))
+    t2 = ctypes.c_void_p()
+    _lib.check(getattr(lib, f"dpr_raster_pullback_host_async_{suf}")(n_in, n_out, garr, P, B, ptr(h["ds_dout"]), ptr(h["points"]),
+               ptr(h["rotation"]), ptr(h["translation"]), ptr(h["out_weight"]), ptr(h["point_weight"]), ptr(g2["points"]),
+               ptr(g2["rotation"]), ptr(g2["translation"]), ptr(g2["background"]), ptr(g2["out_weight"]), ptr(g2["point_weight"]),
+               ctypes.byref(t2)))
+    _lib.check(lib.dpr_host_wait(t2))
+    _lib.check(lib.dpr_host_wait(ticket))
+    assert rel_l2(out2, out_ref) <= TOL[dtype]
+    for k in FIELDS:
+        assert rel_l2(g2[k], getattr(pb_ref, k)) <= TOL[dtype], k
+    bad = ctypes.c_void_p()            # errors of the helper thread come back through the wait
+    _lib.check(getattr(lib, f"dpr_raster_forward_host_async_{suf}")(n_in, n_out, garr, P, B, None, ptr(h["rotation"]),
+               ptr(h["translation"]), None, None, None, ptr(out2), ctypes.byref(bad)))
+    assert lib.dpr_host_wait(bad) == -3
     lib.dpr_host_release()
 
 
