@@ -36,7 +36,7 @@
 namespace dpr {
 namespace t3 {
 
-constexpr int TX = 32, TY = 16, TZ = 16;          // tile extent in cells (x contiguous: one 128-byte line per Float32 row)
+constexpr int TX = 32, TY = 32, TZ = 16;          // tile extent in cells (x contiguous: one 128-byte line per Float32 row)
 constexpr int kTileCells = TX * TY * TZ;
 constexpr int kThreads = 256;
 constexpr uint32_t kNoKey = 0xffffffffu;
@@ -496,21 +496,29 @@ __device__ __forceinline__ long long block_sum_i64(long long v, long long* scrat
     return t;
 }
 
-// Thread <-> tile cell mapping of the flush / tile sums: 16-byte piece r (r = 0 .. kPieces-1) of thread tid is
-// (x4, y, z0 + r * kZStep) with everything but z fixed per thread - no division in the loops.
+// Thread <-> tile cell mapping of the flush / tile sums: 16-byte piece r (r = 0 .. kPieces-1) of thread tid is the piece with
+// linear index tid + r * kThreads of the x-contiguous tile, i.e. cell (x4, y0 + dy(r), z0 + dz(r)) with x4, y0, z0 fixed per
+// thread and dy, dz compile-time functions of r - no division in the loops.
 template <typename T>
 struct CellMap {
     static constexpr int VEC = 16 / sizeof(T);
     static constexpr int PX = TX / VEC;                            // pieces per row
+    static constexpr int kPlanePieces = PX * TY;
     static constexpr int kPieces = kTileCells / VEC / kThreads;    // per thread
-    static constexpr int kZStep = kThreads / (PX * TY);            // z advance per r
-    static_assert(kThreads % (PX * TY) == 0 && kPieces * kZStep == TZ, "tile / CTA shape mismatch");
+    static constexpr bool kMultiY = kPlanePieces > kThreads;       // a plane has more pieces than the CTA has threads
+    static constexpr int RY = kMultiY ? kPlanePieces / kThreads : 1;          // pieces per plane and thread
+    static constexpr int YS = kThreads / PX;                                   // their distance in y
+    static constexpr int kZStep = kMultiY ? 1 : kThreads / kPlanePieces;
+    static_assert(kThreads % PX == 0 && (kMultiY ? kPlanePieces % kThreads == 0 : kThreads % kPlanePieces == 0) &&
+                  kPieces * kThreads * VEC == kTileCells, "tile / CTA shape mismatch");
+    static constexpr __host__ __device__ int dy(int r) { return kMultiY ? (r % RY) * YS : 0; }
+    static constexpr __host__ __device__ int dz(int r) { return kMultiY ? r / RY : r * kZStep; }
     int x4, y, z0;
     __device__ __forceinline__ CellMap() {
         const int tid = threadIdx.x;
         x4 = (tid % PX) * VEC;
-        y = (tid / PX) % TY;
-        z0 = tid / (PX * TY);
+        y = kMultiY ? tid / PX : (tid / PX) % TY;
+        z0 = kMultiY ? 0 : tid / kPlanePieces;
     }
 };
 
@@ -537,8 +545,11 @@ struct FwdTile {
     static constexpr int SIZE = TZ * PLANE;                 // elements
 };
 
+// CTAs per SM the shared-memory tile allows (227 KB per SM, 1 KB reserved per CTA), at most 5: the register budget follows
+constexpr int resident_ctas(size_t tile_bytes) { return (int)((227 * 1024) / (tile_bytes + 2048)) < 5 ? (int)((227 * 1024) / (tile_bytes + 2048)) : 5; }
+
 template <typename T, int N_IN>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 5 : 2)
+__global__ void __launch_bounds__(kThreads, resident_ctas(sizeof(T) * FwdTile<T>::SIZE))
 fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt,
                   const T* __restrict__ rotation, const T* __restrict__ translation, const T* __restrict__ background,
                   const T* __restrict__ out_weight, T* __restrict__ out, Grid<T, 3> grid, TileGeom tg, int64_t b0,
@@ -546,7 +557,7 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
     using CM = CellMap<T>;
     using FT = FwdTile<T>;
     // this kernel runs after the binning kernels of the call: the cached bins are complete (see CacheHeader)
-    if (cache_valid && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *cache_valid = 1ull;
+    if (threadIdx.x == 0 && cache_valid && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) *cache_valid = 1ull;
     constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -566,9 +577,9 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
     const int64_t plane = (int64_t)grid.g[0] * grid.g[1];
     T* const my_cells = tile + (cm.z0 * FT::PLANE + cm.y * FT::PITCH + cm.x4);      // + r * kZStep * PLANE
     T* __restrict__ dst0 = out + b * grid.cells + ((int64_t)(oz + cm.z0) * grid.g[1] + (oy + cm.y)) * grid.g[0] + (ox + cm.x4);
-    const bool col_ok = ox + cm.x4 < grid.g[0] && oy + cm.y < grid.g[1];
+    const bool col_ok = ox + cm.x4 < grid.g[0];
     const bool full_vec = vec_ok && ox + cm.x4 + VEC <= grid.g[0];
-    const int z_lim = grid.g[2] - oz - cm.z0;            // piece r is inside the volume iff r * kZStep < z_lim
+    const int y_lim = grid.g[1] - oy - cm.y, z_lim = grid.g[2] - oz - cm.z0;    // piece r is inside the volume iff dy(r) < y_lim, dz(r) < z_lim
     float inv_q = 0.f;
 
     // stores value(cell) + bg for this thread's cells inside the volume.
@@ -577,15 +588,15 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
     auto flush = [&](auto mode_tag) -> long long {
         constexpr int MODE = decltype(mode_tag)::value;
         unsigned long long cells = 0;
-        T* dst = dst0;
 #pragma unroll
-        for (int r = 0; r < CM::kPieces; ++r, dst += CM::kZStep * plane) {
+        for (int r = 0; r < CM::kPieces; ++r) {
+            T* dst = dst0 + (CM::dz(r) * plane + (int64_t)CM::dy(r) * grid.g[0]);
             Pack pk;
             if constexpr (MODE == 0) {
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) pk.v[k] = bg;
             } else {
-                Pack* cell = reinterpret_cast<Pack*>(my_cells + r * CM::kZStep * FT::PLANE);
+                Pack* cell = reinterpret_cast<Pack*>(my_cells + CM::dz(r) * FT::PLANE + CM::dy(r) * FT::PITCH);
                 pk = *cell;
                 if constexpr (MODE >= 2 && sizeof(T) == 4) {
                     if constexpr (MODE == 3) {
@@ -605,7 +616,7 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
                     for (int k = 0; k < VEC; ++k) pk.v[k] += bg;
                 }
             }
-            if (!col_ok || r * CM::kZStep >= z_lim) continue;
+            if (!col_ok || CM::dy(r) >= y_lim || CM::dz(r) >= z_lim) continue;
             if (full_vec) {
                 __stcs(reinterpret_cast<float4*>(dst), *reinterpret_cast<const float4*>(&pk));
             } else {
@@ -621,7 +632,7 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
             Pack z;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) z.v[k] = T(0);
-            *reinterpret_cast<Pack*>(my_cells + r * CM::kZStep * FT::PLANE) = z;
+            *reinterpret_cast<Pack*>(my_cells + CM::dz(r) * FT::PLANE + CM::dy(r) * FT::PITCH) = z;
         }
     };
     zero_tile();         // (also the padding stays untouched: it is never read)
@@ -809,7 +820,7 @@ __device__ __forceinline__ void red_add4(Pt4<double>* addr, double a, double b, 
 }
 
 template <typename T, int N_IN, bool USE_TMA>
-__global__ void __launch_bounds__(kThreads, sizeof(T) == 4 ? 4 : 2)
+__global__ void __launch_bounds__(kThreads, resident_ctas(sizeof(T) * kTileCells) < 4 ? resident_ctas(sizeof(T) * kTileCells) : 4)
 pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restrict__ ds_dout, const Pt4<T>* __restrict__ pts4,
                        const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt, const T* __restrict__ rotation,
                        const T* __restrict__ translation, const T* __restrict__ out_weight, Pt4<T>* __restrict__ acc4,
@@ -818,7 +829,7 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
                        unsigned long long* __restrict__ cache_valid) {
     constexpr int NR = 3 * N_IN, NV = NR + 3 + 1;     // d_rotation (col-major 3 x N_IN), d_translation, d_out_weight
     using CM = CellMap<T>;
-    if (cache_valid && threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) *cache_valid = 1ull;
+    if (threadIdx.x == 0 && cache_valid && (blockIdx.x | blockIdx.y | blockIdx.z) == 0) *cache_valid = 1ull;
     constexpr int VEC = CM::VEC;
     struct alignas(16) Pack { T v[VEC]; };
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -846,7 +857,7 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
         const bool vec_ok = (grid.g[0] % VEC) == 0 && (reinterpret_cast<uintptr_t>(ds_dout) % 16) == 0;
 #pragma unroll
         for (int r = 0; r < CM::kPieces; ++r) {
-            const int gx = ox + cm.x4, gy = oy + cm.y, gz = oz + cm.z0 + r * CM::kZStep;
+            const int gx = ox + cm.x4, gy = oy + cm.y + CM::dy(r), gz = oz + cm.z0 + CM::dz(r);
             Pack pk;
 #pragma unroll
             for (int k = 0; k < VEC; ++k) pk.v[k] = T(0);
@@ -1107,8 +1118,9 @@ static int cache_begin(CacheCtl& ctl, char* ws, const Plan& pl, int n_in, const 
     fold((unsigned long long)grid[0]); fold((unsigned long long)grid[1]); fold((unsigned long long)grid[2]);
     fold(point_weight ? 1ull : 0ull); fold((unsigned long long)pl.total);
     const int64_t n = P * n_in + (point_weight ? P : 0) + B * 3 * n_in + B * 3;
+    // few, long-running CTAs: every CTA ends with two atomics on the same two words (3000 CTAs made that 15 us)
     int64_t blocks = (n + 256 * 4 - 1) / (256 * 4);
-    if (blocks > (int64_t)dev.sm_count * 32) blocks = (int64_t)dev.sm_count * 32;
+    if (blocks > (int64_t)dev.sm_count * 4) blocks = (int64_t)dev.sm_count * 4;
     if (blocks < 1) blocks = 1;
     {
         LaunchScope scope("tile3_cache_hash", stream);
