@@ -33,17 +33,19 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str | None = None, defines: tuple = ()) -> str:
+    """out / defines: experiment builds (tools/): another output file, extra -D flags; the product is always LIB."""
+    if out is None and not force and not needs_build():
         return LIB
-    cmd = [nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd = ([nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-o", out or LIB]
+           + [os.path.join(CSRC, s) for s in SOURCES])
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libdpr.so")
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":

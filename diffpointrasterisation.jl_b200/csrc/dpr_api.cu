@@ -267,12 +267,14 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) cells *= grid[k];
     const int64_t cb = host_chunk_poses(cells, B, sizeof(T));
+    // The per-pose vectors of the WHOLE batch are copied once, up front (a few hundred KB): small copies issued per chunk
+    // would queue behind a concurrent call's 64 MB copies in the same direction of the host link and stall this pipeline.
     const size_t pts_bytes = align256(sizeof(T) * (size_t)(P * n_in)), pw_bytes = align256(sizeof(T) * (size_t)P);
-    rc = arena_reserve(ar->shared, ar->shared_bytes, pts_bytes + pw_bytes + 256);
+    const size_t rot_b = align256(sizeof(T) * (size_t)(B * n_out * n_in)), tr_b = align256(sizeof(T) * (size_t)(B * n_out));
+    const size_t vec_b = align256(sizeof(T) * (size_t)B), img_b = align256(sizeof(T) * (size_t)(cb * cells));
+    rc = arena_reserve(ar->shared, ar->shared_bytes, pts_bytes + pw_bytes + rot_b + tr_b + 2 * vec_b + 256);
     if (rc != DPR_OK) return rc;
-    const size_t rot_b = align256(sizeof(T) * (size_t)(cb * n_out * n_in)), tr_b = align256(sizeof(T) * (size_t)(cb * n_out));
-    const size_t vec_b = align256(sizeof(T) * (size_t)cb), img_b = align256(sizeof(T) * (size_t)(cb * cells));
-    const size_t need = rot_b + tr_b + 2 * vec_b + img_b;
+    const size_t need = img_b;
     if (need > ar->slot_bytes) {
         size_t have = 0;
         for (int i = 0; i < NSTREAM; ++i) { have = ar->slot_bytes; rc = arena_reserve(ar->slot[i], have, need); if (rc != DPR_OK) return rc; }
@@ -286,35 +288,36 @@ static int forward_host(int n_in, int n_out, const int64_t* grid, int64_t P, int
             ar->ws_bytes = have;
         }
     }
-    T* d_points = static_cast<T*>(ar->shared);
-    T* d_pw = reinterpret_cast<T*>(static_cast<char*>(ar->shared) + pts_bytes);
+    char* sh = static_cast<char*>(ar->shared);
+    T* d_points = reinterpret_cast<T*>(sh);
+    T* d_pw = reinterpret_cast<T*>(sh + pts_bytes);
+    T* d_rot = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes);
+    T* d_tr = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + rot_b);
+    T* d_bg = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + rot_b + tr_b);
+    T* d_ow = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + rot_b + tr_b + vec_b);
     cudaStream_t s0 = ar->streams[0];
-    if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_points, points, sizeof(T) * (size_t)(P * n_in), cudaMemcpyHostToDevice, s0));
-    if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
-    DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
-    int64_t chunk = 0;
     // never return (DPR_CUDA_TRY) with copies into the caller's buffers still in flight
     struct Drain {
         HostArena* ar;
         ~Drain() { for (int i = 0; i < NSTREAM; ++i) cudaStreamSynchronize(ar->streams[i]); }
     } drain{ar};
+    if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_points, points, sizeof(T) * (size_t)(P * n_in), cudaMemcpyHostToDevice, s0));
+    if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
+    DPR_CUDA_TRY(cudaMemcpyAsync(d_rot, rotation, sizeof(T) * (size_t)(B * n_out * n_in), cudaMemcpyHostToDevice, s0));
+    DPR_CUDA_TRY(cudaMemcpyAsync(d_tr, translation, sizeof(T) * (size_t)(B * n_out), cudaMemcpyHostToDevice, s0));
+    if (background) DPR_CUDA_TRY(cudaMemcpyAsync(d_bg, background, sizeof(T) * (size_t)B, cudaMemcpyHostToDevice, s0));
+    if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight, sizeof(T) * (size_t)B, cudaMemcpyHostToDevice, s0));
+    DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
+    int64_t chunk = 0;
     for (int64_t b0 = 0; b0 < B; b0 += cb, ++chunk) {
         const int64_t nb = (b0 + cb < B) ? cb : B - b0;
         const int si = (int)(chunk % NSTREAM);
         cudaStream_t st = ar->streams[si];
-        char* base = static_cast<char*>(ar->slot[si]);
-        T* d_rot = reinterpret_cast<T*>(base);
-        T* d_tr = reinterpret_cast<T*>(base + rot_b);
-        T* d_bg = reinterpret_cast<T*>(base + rot_b + tr_b);
-        T* d_ow = reinterpret_cast<T*>(base + rot_b + tr_b + vec_b);
-        T* d_out = reinterpret_cast<T*>(base + rot_b + tr_b + 2 * vec_b);
+        T* d_out = static_cast<T*>(ar->slot[si]);
         DPR_CUDA_TRY(cudaStreamWaitEvent(st, ar->shared_ready, 0));
-        DPR_CUDA_TRY(cudaMemcpyAsync(d_rot, rotation + b0 * n_out * n_in, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyHostToDevice, st));
-        DPR_CUDA_TRY(cudaMemcpyAsync(d_tr, translation + b0 * n_out, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyHostToDevice, st));
-        if (background) DPR_CUDA_TRY(cudaMemcpyAsync(d_bg, background + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
-        if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
-        rc = forward_entry<T>(n_in, n_out, grid, P, nb, d_points, d_rot, d_tr, background ? d_bg : nullptr,
-                              out_weight ? d_ow : nullptr, point_weight ? d_pw : nullptr, d_out, ar->ws[si], ar->ws_bytes, st);
+        rc = forward_entry<T>(n_in, n_out, grid, P, nb, d_points, d_rot + b0 * n_out * n_in, d_tr + b0 * n_out,
+                              background ? d_bg + b0 : nullptr, out_weight ? d_ow + b0 : nullptr, point_weight ? d_pw : nullptr,
+                              d_out, ar->ws[si], ar->ws_bytes, st);
         if (rc != DPR_OK) break;
         DPR_CUDA_TRY(cudaMemcpyAsync(out + b0 * cells, d_out, sizeof(T) * (size_t)(nb * cells), cudaMemcpyDeviceToHost, st));
     }
@@ -349,14 +352,17 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
     int64_t cells = 1;
     for (int k = 0; k < n_out; ++k) cells *= grid[k];
     const int64_t cb = B > 0 ? host_chunk_poses(cells, B, sizeof(T)) : 1;
-    // shared: points, point_weight, total d_points (+d_point_weight), and one partial buffer per stream
+    // shared: points, point_weight, total d_points (+d_point_weight), one partial buffer per stream, and the per-pose
+    // vectors of the WHOLE batch in both directions: they cross the host link once (inputs up front, gradients at the end)
+    // instead of chunk by chunk, where they would queue behind a concurrent call's 64 MB copies.
     const size_t pts_bytes = align256(sizeof(T) * (size_t)(P * n_in)), pw_bytes = align256(sizeof(T) * (size_t)P);
     const size_t grad_bytes = pts_bytes + pw_bytes;
-    rc = arena_reserve(ar->shared, ar->shared_bytes, pts_bytes + pw_bytes + grad_bytes * (1 + NSTREAM) + 256);
+    const size_t rot_b = align256(sizeof(T) * (size_t)(B * n_out * n_in)), tr_b = align256(sizeof(T) * (size_t)(B * n_out));
+    const size_t vec_b = align256(sizeof(T) * (size_t)B), img_b = align256(sizeof(T) * (size_t)(cb * cells));
+    const size_t pose_b = 2 * rot_b + 2 * tr_b + 3 * vec_b;
+    rc = arena_reserve(ar->shared, ar->shared_bytes, pts_bytes + pw_bytes + grad_bytes * (1 + NSTREAM) + pose_b + 256);
     if (rc != DPR_OK) return rc;
-    const size_t rot_b = align256(sizeof(T) * (size_t)(cb * n_out * n_in)), tr_b = align256(sizeof(T) * (size_t)(cb * n_out));
-    const size_t vec_b = align256(sizeof(T) * (size_t)cb), img_b = align256(sizeof(T) * (size_t)(cb * cells));
-    const size_t need = 2 * rot_b + 2 * tr_b + 3 * vec_b + img_b;
+    const size_t need = img_b;
     if (need > ar->slot_bytes) {
         size_t have = 0;
         for (int i = 0; i < NSTREAM; ++i) { have = ar->slot_bytes; rc = arena_reserve(ar->slot[i], have, need); if (rc != DPR_OK) return rc; }
@@ -375,12 +381,15 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
     T* d_pw = reinterpret_cast<T*>(sh + pts_bytes);
     T* tot_dp = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes);
     T* tot_dpw = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + pts_bytes);
+    char* pose = sh + pts_bytes + pw_bytes + grad_bytes * (1 + NSTREAM);
+    T* d_rot = reinterpret_cast<T*>(pose);
+    T* d_tr = reinterpret_cast<T*>(pose + rot_b);
+    T* d_ow = reinterpret_cast<T*>(pose + rot_b + tr_b);
+    T* g_rot = reinterpret_cast<T*>(pose + rot_b + tr_b + vec_b);
+    T* g_tr = reinterpret_cast<T*>(pose + 2 * rot_b + tr_b + vec_b);
+    T* g_bg = reinterpret_cast<T*>(pose + 2 * rot_b + 2 * tr_b + vec_b);
+    T* g_ow = reinterpret_cast<T*>(pose + 2 * rot_b + 2 * tr_b + 2 * vec_b);
     cudaStream_t s0 = ar->streams[0];
-    if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_points, points, sizeof(T) * (size_t)(P * n_in), cudaMemcpyHostToDevice, s0));
-    if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
-    DPR_CUDA_TRY(cudaMemsetAsync(tot_dp, 0, grad_bytes, s0));
-    DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
-    int64_t chunk = 0;
     // events are destroyed and the streams drained on every exit path, including the early returns of DPR_CUDA_TRY
     struct Cleanup {
         HostArena* ar;
@@ -391,34 +400,30 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
         }
     } cleanup{ar};
     cudaEvent_t (&done)[NSTREAM] = cleanup.done;
+    if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_points, points, sizeof(T) * (size_t)(P * n_in), cudaMemcpyHostToDevice, s0));
+    if (point_weight && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(d_pw, point_weight, sizeof(T) * (size_t)P, cudaMemcpyHostToDevice, s0));
+    if (B > 0) {
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_rot, rotation, sizeof(T) * (size_t)(B * n_out * n_in), cudaMemcpyHostToDevice, s0));
+        DPR_CUDA_TRY(cudaMemcpyAsync(d_tr, translation, sizeof(T) * (size_t)(B * n_out), cudaMemcpyHostToDevice, s0));
+        if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight, sizeof(T) * (size_t)B, cudaMemcpyHostToDevice, s0));
+    }
+    DPR_CUDA_TRY(cudaMemsetAsync(tot_dp, 0, grad_bytes, s0));
+    DPR_CUDA_TRY(cudaEventRecord(ar->shared_ready, s0));
+    int64_t chunk = 0;
     for (int64_t b0 = 0; b0 < B && rc == DPR_OK; b0 += cb, ++chunk) {
         const int64_t nb = (b0 + cb < B) ? cb : B - b0;
         const int si = (int)(chunk % NSTREAM);
         cudaStream_t st = ar->streams[si];
-        char* base = static_cast<char*>(ar->slot[si]);
-        T* d_rot = reinterpret_cast<T*>(base);
-        T* d_tr = reinterpret_cast<T*>(base + rot_b);
-        T* d_ow = reinterpret_cast<T*>(base + rot_b + tr_b);
-        T* g_rot = reinterpret_cast<T*>(base + rot_b + tr_b + vec_b);
-        T* g_tr = reinterpret_cast<T*>(base + 2 * rot_b + tr_b + vec_b);
-        T* g_bg = reinterpret_cast<T*>(base + 2 * rot_b + 2 * tr_b + vec_b);
-        T* g_ow = reinterpret_cast<T*>(base + 2 * rot_b + 2 * tr_b + 2 * vec_b);
-        T* d_img = reinterpret_cast<T*>(base + 2 * rot_b + 2 * tr_b + 3 * vec_b);
+        T* d_img = static_cast<T*>(ar->slot[si]);
         T* part_dp = reinterpret_cast<T*>(sh + pts_bytes + pw_bytes + grad_bytes * (1 + si));
         T* part_dpw = reinterpret_cast<T*>(reinterpret_cast<char*>(part_dp) + pts_bytes);
         DPR_CUDA_TRY(cudaStreamWaitEvent(st, ar->shared_ready, 0));
         DPR_CUDA_TRY(cudaMemcpyAsync(d_img, ds_dout + b0 * cells, sizeof(T) * (size_t)(nb * cells), cudaMemcpyHostToDevice, st));
-        DPR_CUDA_TRY(cudaMemcpyAsync(d_rot, rotation + b0 * n_out * n_in, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyHostToDevice, st));
-        DPR_CUDA_TRY(cudaMemcpyAsync(d_tr, translation + b0 * n_out, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyHostToDevice, st));
-        if (out_weight) DPR_CUDA_TRY(cudaMemcpyAsync(d_ow, out_weight + b0, sizeof(T) * (size_t)nb, cudaMemcpyHostToDevice, st));
-        rc = pullback_entry<T>(n_in, n_out, grid, P, nb, d_img, d_points, d_rot, d_tr, out_weight ? d_ow : nullptr,
-                               point_weight ? d_pw : nullptr, part_dp, g_rot, g_tr, h_dbg ? g_bg : nullptr,
-                               h_dow ? g_ow : nullptr, h_dpw ? part_dpw : nullptr, ar->ws[si], ar->ws_bytes, st);
+        rc = pullback_entry<T>(n_in, n_out, grid, P, nb, d_img, d_points, d_rot + b0 * n_out * n_in, d_tr + b0 * n_out,
+                               out_weight ? d_ow + b0 : nullptr, point_weight ? d_pw : nullptr, part_dp, g_rot + b0 * n_out * n_in,
+                               g_tr + b0 * n_out, h_dbg ? g_bg + b0 : nullptr, h_dow ? g_ow + b0 : nullptr,
+                               h_dpw ? part_dpw : nullptr, ar->ws[si], ar->ws_bytes, st);
         if (rc != DPR_OK) break;
-        DPR_CUDA_TRY(cudaMemcpyAsync(h_drot + b0 * n_out * n_in, g_rot, sizeof(T) * (size_t)(nb * n_out * n_in), cudaMemcpyDeviceToHost, st));
-        DPR_CUDA_TRY(cudaMemcpyAsync(h_dtr + b0 * n_out, g_tr, sizeof(T) * (size_t)(nb * n_out), cudaMemcpyDeviceToHost, st));
-        if (h_dbg) DPR_CUDA_TRY(cudaMemcpyAsync(h_dbg + b0, g_bg, sizeof(T) * (size_t)nb, cudaMemcpyDeviceToHost, st));
-        if (h_dow) DPR_CUDA_TRY(cudaMemcpyAsync(h_dow + b0, g_ow, sizeof(T) * (size_t)nb, cudaMemcpyDeviceToHost, st));
         // fold this chunk's pose-sum into the total on stream 0 (serialises the adds, keeps them race-free)
         if (!done[si]) DPR_CUDA_TRY(cudaEventCreateWithFlags(&done[si], cudaEventDisableTiming));
         DPR_CUDA_TRY(cudaEventRecord(done[si], st));
@@ -439,6 +444,13 @@ static int pullback_host(int n_in, int n_out, const int64_t* grid, int64_t P, in
         if (e != cudaSuccess && rc == DPR_OK) rc = cuda_fail(e, "cudaStreamSynchronize");
     }
     if (rc == DPR_OK) {
+        // stream 0 has waited for every chunk (the fold above), so the per-pose gradients of the whole batch are complete
+        if (B > 0) {
+            DPR_CUDA_TRY(cudaMemcpyAsync(h_drot, g_rot, sizeof(T) * (size_t)(B * n_out * n_in), cudaMemcpyDeviceToHost, s0));
+            DPR_CUDA_TRY(cudaMemcpyAsync(h_dtr, g_tr, sizeof(T) * (size_t)(B * n_out), cudaMemcpyDeviceToHost, s0));
+            if (h_dbg) DPR_CUDA_TRY(cudaMemcpyAsync(h_dbg, g_bg, sizeof(T) * (size_t)B, cudaMemcpyDeviceToHost, s0));
+            if (h_dow) DPR_CUDA_TRY(cudaMemcpyAsync(h_dow, g_ow, sizeof(T) * (size_t)B, cudaMemcpyDeviceToHost, s0));
+        }
         if (P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(h_dp, tot_dp, sizeof(T) * (size_t)(P * n_in), cudaMemcpyDeviceToHost, s0));
         if (h_dpw && P > 0) DPR_CUDA_TRY(cudaMemcpyAsync(h_dpw, tot_dpw, sizeof(T) * (size_t)P, cudaMemcpyDeviceToHost, s0));
     }

@@ -36,9 +36,25 @@
 namespace dpr {
 namespace t3 {
 
-constexpr int TX = 32, TY = 32, TZ = 16;          // tile extent in cells (x contiguous: one 128-byte line per Float32 row)
+#ifndef DPR_T3_TY
+#define DPR_T3_TY 32
+#endif
+#ifndef DPR_T3_TZ
+#define DPR_T3_TZ 16
+#endif
+#ifndef DPR_T3_THREADS
+#define DPR_T3_THREADS 256
+#endif
+#ifndef DPR_T3_BATCH
+#define DPR_T3_BATCH 4
+#endif
+#ifndef DPR_T3_MAXCTAS
+#define DPR_T3_MAXCTAS 4
+#endif
+constexpr int TX = 32, TY = DPR_T3_TY, TZ = DPR_T3_TZ;   // tile extent in cells (x contiguous: one 128-byte line per Float32 row)
 constexpr int kTileCells = TX * TY * TZ;
-constexpr int kThreads = 256;
+constexpr int kThreads = DPR_T3_THREADS;
+constexpr int kBatch = DPR_T3_BATCH;              // entries (and then points) a thread has in flight at once
 constexpr uint32_t kNoKey = 0xffffffffu;
 
 template <typename T>
@@ -62,11 +78,6 @@ struct CacheHeader {
 };
 constexpr unsigned long long kCacheMagic = 0x4450523354494c45ull;   // "DPR3TILE"
 
-__device__ __forceinline__ unsigned long long mix64(unsigned long long z) {      // splitmix64 finaliser
-    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
-    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
-    return z ^ (z >> 31);
-}
 template <typename T>
 __device__ __forceinline__ unsigned long long raw_bits(T v) {
     if constexpr (sizeof(T) == 4) return (unsigned long long)__float_as_uint((float)v);
@@ -96,9 +107,12 @@ __global__ void __launch_bounds__(256) hash_inputs_kernel(const T* __restrict__ 
             const int64_t i = i0 + u * stride;
             if (i >= n) continue;
             // position-dependent terms, summed: independent of the order of the threads, dependent on the order of the data
-            const unsigned long long t = mix64(raw_bits(v[u]) + (unsigned long long)(i + 1) * 0x9e3779b97f4a7c15ull);
+            // (two multiply-xorshift rounds per element; the full splitmix64 finaliser on both words made this pass 15 us)
+            unsigned long long t = (raw_bits(v[u]) ^ ((unsigned long long)(i + 1) * 0x9e3779b97f4a7c15ull)) * 0xbf58476d1ce4e5b9ull;
+            t ^= t >> 29;
             h1 += t;
-            h2 += mix64(t ^ 0xd6e8feb86659fd93ull);
+            t *= 0x94d049bb133111ebull;
+            h2 += t ^ (t >> 32);
         }
     }
 #pragma unroll
@@ -293,7 +307,7 @@ __global__ void __launch_bounds__(256) sort_scatter4_kernel(const T* __restrict_
         q.z = N_IN > 2 ? __ldg(points + p * N_IN + (N_IN > 2 ? 2 : 0)) : T(0);
         q.w = point_weight ? __ldg(point_weight + p) : T(1);
         pts4[pos] = q;
-        perm[pos] = (int32_t)p;
+        perm[p] = (int32_t)pos;         // INVERSE permutation (coalesced store): original index -> sorted position
         const float w = (float)q.w;
         bad = bad || !(w >= 0.f) || !(w < 3e38f);     // negative, NaN or infinite weights: no fixed-point accumulation
         wmax = fmaxf(wmax, w);
@@ -334,16 +348,19 @@ __device__ __forceinline__ void load_xyz(T (&x)[N_IN], const Pt4<T>& q) {
 // key of one (point, pose) pair from the lower-corner cell i0 (already validated by stencil(): -1 <= i0 <= g - 1)
 __device__ __forceinline__ uint32_t tile_key(const int (&i0)[3], const int (&g)[3], const TileGeom& tg, int pose_local) {
     constexpr int TS[3] = {TX, TY, TZ};
-    int home[3];
+    unsigned home[3];
     unsigned pat = 0;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const bool lo_ok = i0[k] >= 0, hi_ok = i0[k] + 1 < g[k];
-        const int t_lo = (lo_ok ? i0[k] : 0) / TS[k], t_hi = (i0[k] + 1) / TS[k];
-        home[k] = lo_ok ? t_lo : t_hi;
-        if (lo_ok && hi_ok && t_hi != t_lo) pat |= 1u << k;
+        // tile of the upper corner (i0 + 1 >= 0) and of the lower one; unsigned divisions by a power of two are shifts.  A lower
+        // corner outside the grid (i0 = -1) makes the upper corner's tile the home, an upper corner outside the grid (or in
+        // the same tile) leaves the pattern bit clear.
+        const unsigned t_hi = (unsigned)(i0[k] + 1) / (unsigned)TS[k];
+        const unsigned t_lo = i0[k] >= 0 ? (unsigned)i0[k] / (unsigned)TS[k] : t_hi;
+        home[k] = t_lo;
+        if (i0[k] + 1 < g[k] && t_hi != t_lo) pat |= 1u << k;
     }
-    const uint32_t tile = (uint32_t)((home[2] * tg.nt[1] + home[1]) * tg.nt[0] + home[0]);
+    const uint32_t tile = (home[2] * (uint32_t)tg.nt[1] + home[1]) * (uint32_t)tg.nt[0] + home[0];
     return (((uint32_t)pose_local * (uint32_t)tg.n_tiles + tile) << 3) | pat;
 }
 
@@ -391,15 +408,20 @@ static __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, uint32_
         const int p = (blockIdx.x * K + k) * 256 + (int)threadIdx.x;
         key[k] = p < P ? __ldg(my_keys + p) : kNoKey;
     }
+    // all K atomics of a thread are in flight before the first result is needed (one L2 round trip, not K)
+    unsigned peers[K];
+    uint32_t base[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+        peers[k] = __match_any_sync(0xffffffffu, key[k]);
+        base[k] = 0;
+        if (key[k] != kNoKey && lane == __ffs(peers[k]) - 1) base[k] = atomicAdd(cnt + key[k], (uint32_t)__popc(peers[k]));
+    }
 #pragma unroll
     for (int k = 0; k < K; ++k) {
         const int p = (blockIdx.x * K + k) * 256 + (int)threadIdx.x;
-        const unsigned peers = __match_any_sync(0xffffffffu, key[k]);
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (key[k] != kNoKey && lane == leader) base = atomicAdd(cnt + key[k], (uint32_t)__popc(peers));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (key[k] != kNoKey) entries[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)p;
+        const uint32_t b = __shfl_sync(0xffffffffu, base[k], __ffs(peers[k]) - 1);
+        if (key[k] != kNoKey) entries[b + __popc(peers[k] & ((1u << lane) - 1u))] = (uint32_t)p;
     }
 }
 
@@ -423,8 +445,19 @@ constexpr int kMaxSlots = 27;
 
 // the 27 (lower-neighbour offset d, pattern) combinations with pattern containing d; combination 0 is the tile's own
 // pattern-0 list (stencils entirely inside the tile)
-__device__ __constant__ unsigned char kComboD[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 7, 0, 0, 0, 0, 0};
-__device__ __constant__ unsigned char kComboPat[32] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 3, 5, 7, 2, 3, 6, 7, 3, 7, 4, 5, 6, 7, 5, 7, 6, 7, 7, 0, 0, 0, 0, 0};
+// (3 bits per lane, packed into immediates: a lane-indexed __constant__ load is serialised per distinct address)
+constexpr unsigned char kComboD[27] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 7};
+constexpr unsigned char kComboPat[27] = {0, 1, 2, 3, 4, 5, 6, 7, 1, 3, 5, 7, 2, 3, 6, 7, 3, 7, 4, 5, 6, 7, 5, 7, 6, 7, 7};
+__host__ __device__ constexpr unsigned long long pack3(const unsigned char (&v)[27], int first, int last) {
+    unsigned long long r = 0;
+    for (int i = first; i < last; ++i) r |= (unsigned long long)v[i] << (3 * (i - first));
+    return r;
+}
+constexpr unsigned long long kComboDLo = pack3(kComboD, 0, 21), kComboDHi = pack3(kComboD, 21, 27);
+constexpr unsigned long long kComboPatLo = pack3(kComboPat, 0, 21), kComboPatHi = pack3(kComboPat, 21, 27);
+__device__ __forceinline__ int combo_lookup(unsigned long long lo, unsigned long long hi, int lane) {
+    return (int)(((lane < 21 ? lo >> (3 * lane) : hi >> (3 * (lane - 21)))) & 7ull);      // lanes >= 27 read zeros
+}
 
 // compact table of the non-empty sub-lists of one item, built by warp 0
 struct SlotTable {
@@ -438,7 +471,8 @@ __device__ __forceinline__ void build_slot_table(SlotTable& tab, const uint32_t*
                                                  int tx, int ty, int tz) {
     if (threadIdx.x >= 32) return;
     const int lane = threadIdx.x;
-    const int d = kComboD[lane], pat = kComboPat[lane];
+    constexpr unsigned long long d_lo = kComboDLo, d_hi = kComboDHi, p_lo = kComboPatLo, p_hi = kComboPatHi;
+    const int d = combo_lookup(d_lo, d_hi, lane), pat = combo_lookup(p_lo, p_hi, lane);
     const int nx = tx - (d & 1), ny = ty - ((d >> 1) & 1), nz = tz - ((d >> 2) & 1);
     uint32_t s = 0, e = 0;
     if (lane < kMaxSlots && nx >= 0 && ny >= 0 && nz >= 0) {
@@ -546,7 +580,7 @@ struct FwdTile {
 };
 
 // CTAs per SM the shared-memory tile allows (227 KB per SM, 1 KB reserved per CTA), at most 5: the register budget follows
-constexpr int resident_ctas(size_t tile_bytes) { return (int)((227 * 1024) / (tile_bytes + 2048)) < 5 ? (int)((227 * 1024) / (tile_bytes + 2048)) : 5; }
+constexpr int resident_ctas(size_t tile_bytes) { return (int)((227 * 1024) / (tile_bytes + 2048)) < DPR_T3_MAXCTAS ? (int)((227 * 1024) / (tile_bytes + 2048)) : DPR_T3_MAXCTAS; }
 
 template <typename T, int N_IN>
 __global__ void __launch_bounds__(kThreads, resident_ctas(sizeof(T) * FwdTile<T>::SIZE))
@@ -676,18 +710,24 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
     // list, whose stencils lie inside the tile (only the volume's faces can still clip them: the checked path)
     auto accumulate = [&](auto fixed_tag) {
         constexpr bool FIXED = decltype(fixed_tag)::value;
-        uint32_t e = threadIdx.x;
-        if (e >= total) return;
+        if (threadIdx.x >= total) return;
         EntryCursor cur;
         cur.init(&tab, entries);
-        const uint32_t idx0 = cur.fetch(e);
-        uint32_t idx_n = e + kThreads < total ? cur.fetch(e + kThreads) : 0u;
-        Pt4<T> qn = pts4[idx0];
         const uint32_t tile_s = smem_u32(tile);
-        for (; e < total; e += kThreads) {
-            const Pt4<T> q = qn;
-            if (e + kThreads < total) qn = pts4[idx_n];
-            if (e + 2 * kThreads < total) idx_n = cur.fetch(e + 2 * kThreads);
+        // kBatch entries, then their kBatch points, are in flight at once: two dependent round trips per batch instead of
+        // two per entry (an item has about four entries per thread, so a rolling prefetch never reaches steady state)
+        for (uint32_t e0 = threadIdx.x; e0 < total; e0 += kBatch * kThreads) {
+            uint32_t idx[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) idx[j] = e0 + j * kThreads < total ? cur.fetch(e0 + j * kThreads) : 0u;
+            Pt4<T> qb[kBatch];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) qb[j] = pts4[idx[j]];
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) {
+            const uint32_t e = e0 + j * kThreads;
+            if (e >= total) break;
+            const Pt4<T> q = qb[j];
             T x[N_IN];
             load_xyz<T, N_IN>(x, q);
             int i0[3];
@@ -737,6 +777,7 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
                 }
             }
             mass += msum;       // 8 values below 2^22 each: no 32-bit overflow inside one entry
+            }
         }
     };
     if constexpr (sizeof(T) == 4) {
@@ -820,7 +861,7 @@ __device__ __forceinline__ void red_add4(Pt4<double>* addr, double a, double b, 
 }
 
 template <typename T, int N_IN, bool USE_TMA>
-__global__ void __launch_bounds__(kThreads, resident_ctas(sizeof(T) * kTileCells) < 4 ? resident_ctas(sizeof(T) * kTileCells) : 4)
+__global__ void __launch_bounds__(kThreads, resident_ctas(sizeof(T) * kTileCells))
 pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restrict__ ds_dout, const Pt4<T>* __restrict__ pts4,
                        const uint32_t* __restrict__ entries, const uint32_t* __restrict__ cnt, const T* __restrict__ rotation,
                        const T* __restrict__ translation, const T* __restrict__ out_weight, Pt4<T>* __restrict__ acc4,
@@ -882,7 +923,9 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
         return;
     }
 
-    // the first entry / point of this thread take off before the tile is waited for
+    // the first entry / point of this thread take off before the tile is waited for.  (Rolling prefetch, one entry and one
+    // point ahead: loading kBatch entries and points at once, as the forward does, leaves the memory pipe idle while the
+    // batch is computed and cost 27 us on config 3 - the TMA wait already hides the first round trips here.)
     EntryCursor cur;
     uint32_t e = threadIdx.x;
     uint32_t idx = 0, idx_n = 0;
@@ -1019,14 +1062,15 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
     }
 }
 
-// 6. packed, sorted-order gradients -> d_points (N_in, P) and d_point_weight (P) in the caller's point order
+// 6. packed, sorted-order gradients -> d_points (N_in, P) and d_point_weight (P) in the caller's point order: a GATHER through
+// the inverse permutation (coalesced stores, 16-byte reads of the L2-resident packed buffer; the scatter through the forward
+// permutation wrote 12-byte pieces at random and took 25 us for 1 M points)
 template <typename T, int N_IN>
-__global__ void __launch_bounds__(256) unpermute_kernel(const Pt4<T>* __restrict__ acc4, const int32_t* __restrict__ perm, int64_t P,
+__global__ void __launch_bounds__(256) unpermute_kernel(const Pt4<T>* __restrict__ acc4, const int32_t* __restrict__ inv_perm, int64_t P,
                                                         T* __restrict__ d_points, T* __restrict__ d_point_weight) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
-        const Pt4<T> a = acc4[i];
-        const int64_t p = perm[i];
+    for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < P; p += stride) {
+        const Pt4<T> a = acc4[__ldg(inv_perm + p)];
         d_points[p * N_IN] = a.x;
         if constexpr (N_IN > 1) d_points[p * N_IN + 1] = a.y;
         if constexpr (N_IN > 2) d_points[p * N_IN + 2] = a.z;
