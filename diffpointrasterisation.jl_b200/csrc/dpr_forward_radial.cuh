@@ -192,6 +192,19 @@ fwd_tile2d_radial_kernel(const float4* __restrict__ pts4, const float* __restric
     const int c_end = (c_begin + chunks_per_split < n_chunks_total) ? c_begin + chunks_per_split : n_chunks_total;
     const int p_begin = c_begin * kChunk, p_end = c_end * kChunk;
 
+    // The first two points of this thread and its first chunk radius depend on nothing but the block index: they are
+    // requested before the pose is loaded, the tile zeroed and the safe radius derived, so those ~2 us of set-up (one CTA
+    // per SM: nothing else hides them) overlap with the loads' latency (config 2: 1.572 -> 1.539 ms).  The copy is padded, so
+    // the prefetch never needs a bounds test (a split that starts beyond the last chunk - (Q-1)*ceil(n/Q) can exceed n - has
+    // no work: its prefetch is clamped into the padding, which covers chunks n .. n+2).
+    // (A persistent variant - one CTA per SM walking the poses, the next pose's parameters staged with cp.async - measured
+    // 1.548 ms: the hardware's dynamic CTA scheduling balances the poses' unequal outer shells better than a static walk.)
+    const float4* __restrict__ next = pts4 + (size_t)(c_begin < n_chunks_total ? c_begin : n_chunks_total) * kChunk + threadIdx.x;
+    float4 pf0 = ldg_stream4(next), pf1 = ldg_stream4(next + kChunk);
+    next += 2 * kChunk;
+    float rmax_first = 0.f;
+    if (c_begin + (int)threadIdx.x < c_end) rmax_first = __ldg(rmax + c_begin + threadIdx.x);
+
     // ---- fixed-point scale (uniform across the CTA); not eligible -> float CAS accumulation (generic code) -----------
     // A contribution v = w * out_weight * point_weight = w * pw' * A with pw' = point_weight * 2^-em in [0, 1] (stored in
     // the packed copy) and A = out_weight * 2^em is accumulated as the integer rint(w * pw' * Q), Q = rint(A * 2^(F - e)),
@@ -239,7 +252,11 @@ fwd_tile2d_radial_kernel(const float4* __restrict__ pts4, const float* __restric
     }
 
     if (threadIdx.x == 0) s_first = c_end;
-    for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile_u[i] = 0u;
+    if ((n_tile & 3) == 0) {
+        for (int i = threadIdx.x; i < n_tile / 4; i += blockDim.x) reinterpret_cast<uint4*>(tile_u)[i] = make_uint4(0u, 0u, 0u, 0u);
+    } else {
+        for (int i = threadIdx.x; i < n_tile; i += blockDim.x) tile_u[i] = 0u;
+    }
     if (tp.exclusive && border) {
         const int lo_cells = band_lo * g0;
         for (int i = threadIdx.x; i < lo_cells; i += blockDim.x) img[i] = bg;
@@ -248,8 +265,10 @@ fwd_tile2d_radial_kernel(const float4* __restrict__ pts4, const float* __restric
     }
     __syncthreads();
     if (fixed) {
-        for (int c = c_begin + (int)threadIdx.x; c < c_end; c += blockDim.x)
-            if (!(__ldg(rmax + c) <= r_safe)) atomicMin(&s_first, c);
+        for (int c = c_begin + (int)threadIdx.x; c < c_end; c += blockDim.x) {
+            const float rm = c == c_begin + (int)threadIdx.x ? rmax_first : __ldg(rmax + c);
+            if (!(rm <= r_safe)) atomicMin(&s_first, c);
+        }
     }
     __syncthreads();
     const int c_safe = s_first;               // chunks [c_begin, c_safe) are interior for this pose
@@ -343,16 +362,11 @@ fwd_tile2d_radial_kernel(const float4* __restrict__ pts4, const float* __restric
         };
 
         // two points in flight per thread (the points stream from L2: one chunk ahead left ~27 % of the stall cycles on
-        // the load's scoreboard); the copy is padded, so the prefetch never needs a bounds test
-        // (a split that starts beyond the last chunk - (Q-1)*ceil(n/Q) can exceed n - has no work: its prefetch is clamped
-        // into the padding, which covers chunks n .. n+2)
-        const float4* __restrict__ next = pts4 + (size_t)(c_begin < n_chunks_total ? c_begin : n_chunks_total) * kChunk + threadIdx.x;
-        float4 q0 = ldg_stream4(next), q1 = ldg_stream4(next + kChunk);
-        next += 2 * kChunk;
+        // the load's scoreboard); pf0, pf1 were requested at the top of the kernel
         auto pop = [&]() -> float4 {
-            const float4 v = q0;
-            q0 = q1;
-            q1 = ldg_stream4(next);
+            const float4 v = pf0;
+            pf0 = pf1;
+            pf1 = ldg_stream4(next);
             next += kChunk;
             return v;
         };
@@ -425,9 +439,9 @@ fwd_tile2d_radial_kernel(const float4* __restrict__ pts4, const float* __restric
         } else {
             for (int i = threadIdx.x; i < n_tile; i += blockDim.x) cells_sum += (unsigned long long)tile_u[i];
         }
-        mass = block_sum_ll(mass, scratch);
-        const long long cells_total = block_sum_ll((long long)cells_sum, scratch);
-        if (cells_total != mass) {
+        // exact: the sum of the cells equals the sum of what was added unless a 32-bit cell wrapped (one reduction of the
+        // difference instead of one per side)
+        if (block_sum_ll((long long)cells_sum - mass, scratch) != 0) {
             // a 32-bit cell wrapped: redo this slab in float (border splats were already sent)
             fixed = false;
             flushed = false;

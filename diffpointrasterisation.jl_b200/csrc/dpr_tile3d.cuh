@@ -88,33 +88,45 @@ __global__ void __launch_bounds__(256) hash_inputs_kernel(const T* __restrict__ 
                                                           const T* __restrict__ rot, int64_t n_rot, const T* __restrict__ tr, int64_t n_tr,
                                                           unsigned long long params, CacheHeader* __restrict__ h) {
     unsigned long long h1 = 0, h2 = 0;
-    const int64_t n = n_pts + n_pw + n_rot + n_tr;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    constexpr int U = 4;                    // independent loads in flight per thread
-    for (int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += U * stride) {
-        T v[U];
+    // position-dependent terms, summed: independent of the order of the threads, dependent on the order of the data.  Two
+    // multiply-xorshift rounds per element (the full splitmix64 finaliser on both words made this pass compute bound).
+    auto term = [&](T v, int64_t i) {
+        unsigned long long t = (raw_bits(v) ^ ((unsigned long long)(i + 1) * 0x9e3779b97f4a7c15ull)) * 0xbf58476d1ce4e5b9ull;
+        t ^= t >> 29;
+        h1 += t;
+        t *= 0x94d049bb133111ebull;
+        h2 += t ^ (t >> 32);
+    };
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) Pack { T v[VEC]; };
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    // one array: elements [0, n) hash at positions base + i.  16-byte loads, two in flight, where the array is aligned
+    // (the value of the hash does not depend on which path read an element)
+    auto hash_array = [&](const T* __restrict__ a, int64_t n, int64_t base) {
+        if (n <= 0) return;
+        int64_t n_vec = 0;
+        if ((reinterpret_cast<uintptr_t>(a) & 15u) == 0) {
+            n_vec = n / VEC;
+            const Pack* __restrict__ av = reinterpret_cast<const Pack*>(a);
+            for (int64_t g = tid; g < n_vec; g += 2 * stride) {
+                const Pack p0 = av[g];
+                Pack p1 = p0;
+                const bool two = g + stride < n_vec;
+                if (two) p1 = av[g + stride];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + u * stride;
-            v[u] = T(0);
-            if (i < n_pts) v[u] = __ldg(points + i);
-            else if (i < n_pts + n_pw) v[u] = __ldg(pw + (i - n_pts));
-            else if (i < n_pts + n_pw + n_rot) v[u] = __ldg(rot + (i - n_pts - n_pw));
-            else if (i < n) v[u] = __ldg(tr + (i - n_pts - n_pw - n_rot));
-        }
+                for (int k = 0; k < VEC; ++k) term(p0.v[k], base + g * VEC + k);
+                if (two) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int64_t i = i0 + u * stride;
-            if (i >= n) continue;
-            // position-dependent terms, summed: independent of the order of the threads, dependent on the order of the data
-            // (two multiply-xorshift rounds per element; the full splitmix64 finaliser on both words made this pass 15 us)
-            unsigned long long t = (raw_bits(v[u]) ^ ((unsigned long long)(i + 1) * 0x9e3779b97f4a7c15ull)) * 0xbf58476d1ce4e5b9ull;
-            t ^= t >> 29;
-            h1 += t;
-            t *= 0x94d049bb133111ebull;
-            h2 += t ^ (t >> 32);
+                    for (int k = 0; k < VEC; ++k) term(p1.v[k], base + (g + stride) * VEC + k);
+                }
+            }
         }
-    }
+        for (int64_t i = n_vec * VEC + tid; i < n; i += stride) term(__ldg(a + i), base + i);
+    };
+    hash_array(points, n_pts, 0);
+    hash_array(pw, n_pw, n_pts);
+    hash_array(rot, n_rot, n_pts + n_pw);
+    hash_array(tr, n_tr, n_pts + n_pw + n_rot);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         h1 += __shfl_xor_sync(0xffffffffu, h1, o);
@@ -395,11 +407,12 @@ __global__ void __launch_bounds__(256) tile_count_kernel(const Pt4<T>* __restric
         if (key != kNoKey && lane == __ffs(peers) - 1) atomicAdd(cnt + key, (uint32_t)__popc(peers));
     }
 }
+constexpr int kScatterK = 8;
 // pass 2 (after the scan): the sorted point index of every pair goes to its list; no transform, the keys are re-read
 static __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, uint32_t* __restrict__ cnt, const uint32_t* __restrict__ keys,
                                                                   uint32_t* __restrict__ entries, const unsigned int* __restrict__ skip) {
     if (skip && *skip) return;                 // binning cache hit (uniform)
-    constexpr int K = 4;
+    constexpr int K = kScatterK;               // the pass is two dependent round trips per CTA: long CTAs, few waves
     const uint32_t* __restrict__ my_keys = keys + (size_t)blockIdx.y * (size_t)P;
     const int lane = threadIdx.x & 31;
     uint32_t key[K];
@@ -1162,9 +1175,9 @@ static int cache_begin(CacheCtl& ctl, char* ws, const Plan& pl, int n_in, const 
     fold((unsigned long long)grid[0]); fold((unsigned long long)grid[1]); fold((unsigned long long)grid[2]);
     fold(point_weight ? 1ull : 0ull); fold((unsigned long long)pl.total);
     const int64_t n = P * n_in + (point_weight ? P : 0) + B * 3 * n_in + B * 3;
-    // few, long-running CTAs: every CTA ends with two atomics on the same two words (3000 CTAs made that 15 us)
-    int64_t blocks = (n + 256 * 4 - 1) / (256 * 4);
-    if (blocks > (int64_t)dev.sm_count * 4) blocks = (int64_t)dev.sm_count * 4;
+    // few, long-running CTAs: every CTA ends with three atomics on the same line (3000 CTAs made that 15 us)
+    int64_t blocks = (n + 256 * 8 - 1) / (256 * 8);
+    if (blocks > (int64_t)dev.sm_count * 2) blocks = (int64_t)dev.sm_count * 2;
     if (blocks < 1) blocks = 1;
     {
         LaunchScope scope("tile3_cache_hash", stream);
@@ -1236,7 +1249,8 @@ static int bin_poses(const T* rotation, const T* translation, const Grid<T, 3>& 
     if (rc != DPR_OK) return rc;
     {
         LaunchScope scope("tile3_bin_scatter", stream);
-        tile_scatter_kernel<<<gridDim3, 256, 0, stream>>>((int)P, cnt, tile_keys, entries, ctl.skip);
+        const dim3 grid_scatter((unsigned)((P + 256 * kScatterK - 1) / (256 * kScatterK)), (unsigned)nb);
+        tile_scatter_kernel<<<grid_scatter, 256, 0, stream>>>((int)P, cnt, tile_keys, entries, ctl.skip);
     }
     DPR_CUDA_TRY(cudaGetLastError());
     return DPR_OK;
