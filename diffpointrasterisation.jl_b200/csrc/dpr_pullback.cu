@@ -475,11 +475,12 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
     const int64_t pose_chunks = (a.B + pose_chunk - 1) / pose_chunk;
     // d_background: a few extra CTAs per pose chunk inside the gather launch (see the kernel) when there is enough
     // gather work to hide them behind, else the separate pass
-    // (one bg CTA sums whole images, about 3 MB of them - the duration of a gather CTA; large images, where that is only
-    // a few poses, and launches with few gather CTAs keep the separate pass: config 4 lost 1.7 ms with 51 MB per bg CTA)
+    // (one bg CTA sums whole images, about 3 MB of them - well below the duration of a gather CTA; images above 8 MB, where
+    // one image alone is a long CTA, and launches with few gather CTAs keep the separate pass: config 4 lost 1.7 ms with
+    // 51 MB per bg CTA)
     int bg_ctas = 0;
     const int64_t img_bytes = grid.cells * (int64_t)sizeof(T);
-    if (a.d_background && img_bytes <= ((int64_t)512 << 10) && point_chunks >= 8 && pose_chunk >= 8) {
+    if (a.d_background && img_bytes <= ((int64_t)8 << 20) && point_chunks >= 8 && pose_chunk >= 8) {
         int64_t n = (pose_chunk * img_bytes + ((int64_t)3 << 20) - 1) / ((int64_t)3 << 20);
         if (n < 1) n = 1;
         if (n > pose_chunk) n = pose_chunk;
