@@ -293,14 +293,30 @@ fwd_splat_tile2d_kernel(const T* __restrict__ points, const T* __restrict__ rota
 __global__ void __launch_bounds__(256) point_weight_stats_partial_kernel(const float* __restrict__ pw, int64_t P,
                                                                          float* __restrict__ partial /* [grid][4] */) {
     float mx = -3.4e38f, mn = 3.4e38f, sum = 0.f;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += stride) {
-        const float w = __ldg(pw + i);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    auto take = [&](float w) {
         mx = fmaxf(mx, w);
         mn = fminf(mn, w);
         sum += w;
         if (!(w == w)) mn = -1.f;    // NaN weights disable the fixed-point mode
+    };
+    // at most 15 CTAs (the partials share the 256-byte statistics block): 16-byte loads, four in flight per thread
+    int64_t n_vec = 0;
+    if ((reinterpret_cast<uintptr_t>(pw) & 15u) == 0) {
+        n_vec = P / 4;
+        const float4* __restrict__ pw4 = reinterpret_cast<const float4*>(pw);
+        for (int64_t i = tid; i < n_vec; i += 4 * stride) {
+            float4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) q[u] = i + u * stride < n_vec ? __ldg(pw4 + i + u * stride) : make_float4(q[0].x, q[0].x, q[0].x, q[0].x);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (i + u * stride >= n_vec) break;
+                take(q[u].x); take(q[u].y); take(q[u].z); take(q[u].w);
+            }
+        }
     }
+    for (int64_t i = n_vec * 4 + tid; i < P; i += stride) take(__ldg(pw + i));
     __shared__ float smx[8], smn[8], ssum[8];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {

@@ -830,15 +830,14 @@ def test_tile3d_binning_cache():
     args = list(dev_args(d, np.float32))
     ds = to_dev(d["ds_dout"], torch.float32)
 
-    def kernels_run(fn):
-        dpr_b200._lib.profile_enable(True)
-        res = fn()
+    def cache_hit():
+        """The device-side decision of the LAST call: word `skip` of the cache header at the start of the workspace
+        (csrc/dpr_tile3d.cuh CacheHeader: magic 8, hash 16, params 8, valid 8, acc 16, done_blocks 4, skip 4 bytes)."""
         torch.cuda.synchronize()
-        rec = dict()
-        for name, ms in dpr_b200._lib.profile_records():
-            rec[name] = rec.get(name, 0.0) + ms
-        dpr_b200._lib.profile_enable(False)
-        return res, rec
+        cur = torch.cuda.current_stream().cuda_stream
+        (ws,) = [b for (_dev, st), b in dpr_b200.interface._workspaces.items()
+                 if st == cur and b.device.index == torch.cuda.current_device()]
+        return int(ws[60:64].view(torch.int32).item()) == 1
 
     def check_out(out):
         assert rel_l2(to_np(out), out_ref) <= 1e-5
@@ -848,36 +847,45 @@ def test_tile3d_binning_cache():
             assert rel_l2(to_np(getattr(pb, k)), getattr(ref, k)) <= 1e-5, k
 
     with forced(forward_algo=3, pullback_algo=7, binning_cache=1):
-        out, r1 = kernels_run(lambda: dpr_b200.raster(grid, *args))
-        check_out(out)
-        pb, r2 = kernels_run(lambda: dpr_b200.raster_pullback_(ds, *args))
-        check_pb(pb)
-        # the pullback's binning kernels returned at once: far cheaper than the forward's (which may itself have hit)
-        out2, r3 = kernels_run(lambda: dpr_b200.raster(grid, *args))
-        check_out(out2)
-        assert r3["tile3_bin_count"] < 0.5 * max(r1["tile3_bin_count"], 1e-3) or r1["tile3_bin_count"] < 0.01
+        # a first call on other inputs, so that whatever an earlier test left in the workspace cannot match
+        pts0 = args[0].clone()
+        pts0[:, 3] -= 0.125
+        dpr_b200.raster(grid, pts0, *args[1:])
+        check_out(dpr_b200.raster(grid, *args))
+        assert not cache_hit()
+        check_pb(dpr_b200.raster_pullback_(ds, *args))
+        assert cache_hit()                               # the pullback reused the forward's bins
+        check_out(dpr_b200.raster(grid, *args))
+        assert cache_hit()
         # a changed point must be seen (miss) ...
         pts2 = args[0].clone()
         pts2[:, 17] += 0.25
         d2 = dict(d, points=to_np(pts2))
         out_ref2, pb_ref2 = _oracle_pair(d2, grid, np.float32)
         pb2 = dpr_b200.raster_pullback_(ds, pts2, *args[1:])
+        assert not cache_hit()
         check_pb(pb2, pb_ref2)
         assert rel_l2(to_np(dpr_b200.raster(grid, pts2, *args[1:])), out_ref2) <= 1e-5
+        assert cache_hit()
         # ... so must a changed pose, and going back to the first inputs
         tr2 = args[2].clone()
         tr2[:, 1] += 0.05
         d3 = dict(d, translation=to_np(tr2))
         out_ref3, _ = _oracle_pair(d3, grid, np.float32)
         assert rel_l2(to_np(dpr_b200.raster(grid, args[0], args[1], tr2, *args[3:])), out_ref3) <= 1e-5
+        assert not cache_hit()
         check_out(dpr_b200.raster(grid, *args))
+        assert not cache_hit()
         check_pb(dpr_b200.raster_pullback_(ds, *args))
+        assert cache_hit()
         # another kernel path (2-d tile kernels, same stream => same workspace) in between invalidates the bins
         d2d = make_inputs(6, 3, 2, 9000, 3, (32, 32), np.float32)
         dpr_b200.raster((32, 32), *dev_args(d2d, np.float32))
         dpr_b200.raster_pullback_(to_dev(d2d["ds_dout"], torch.float32), *dev_args(d2d, np.float32))
         check_pb(dpr_b200.raster_pullback_(ds, *args))
+        assert not cache_hit()
         check_out(dpr_b200.raster(grid, *args))
+        assert cache_hit()
     with forced(forward_algo=3, pullback_algo=7, binning_cache=0):
         check_out(dpr_b200.raster(grid, *args))
         check_pb(dpr_b200.raster_pullback_(ds, *args))
