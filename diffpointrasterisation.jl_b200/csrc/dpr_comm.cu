@@ -73,8 +73,12 @@ static int nccl_fail(ncclResult_t r, const char* what) {
 // ---- one-shot all-reduce over peer memory ---------------------------------------------------------------------------
 constexpr int kMaxRanks = 16;
 constexpr size_t kP2pCapacity = (size_t)16 << 20;     // payload bytes per call served by the peer-memory path
-constexpr size_t kFlagsBytes = 4096;                  // [rank] x 128-byte flag slots, then the CTA counter at byte 2048
-constexpr size_t kCounterOffset = 2048;
+constexpr size_t kFlagsBytes = 8192;                  // "published" flags: [rank] x 128-byte slots; CTA counters at 2048 and 2176;
+constexpr size_t kCounterOffset = 2048;               // "slice reduced" flags (two-shot): 4096 + [rank] x 128
+constexpr size_t kCounter2Offset = 2176;
+constexpr size_t kFlagsBOffset = 4096;
+// two-shot (reduce-scatter + all-gather) instead of one-shot once the one-shot's peer reads exceed this many bytes per rank
+constexpr size_t kTwoShotPeerBytes = (size_t)32 << 20;
 
 struct PeerTable {
     char* base[kMaxRanks];        // symmetric buffer of every rank as mapped into this process (base[rank] = own)
@@ -169,6 +173,105 @@ __global__ void __launch_bounds__(512) allreduce_reduce_kernel(T* __restrict__ b
     }
 }
 
+// Two-shot variant for large payloads on many ranks (the one-shot kernel reads (n - 1) x payload over NVLink per rank:
+// 112 MB for 16 MB on 8 ranks, 0.19 ms; two shots read 2 x (n - 1) / n x payload = 28 MB).  After the same publish kernel:
+//   reduce-scatter: rank r sums slice r of every rank's buffer (rank order), stores it into slice r of its OWN symmetric
+//                   buffer - no peer reads that slice before the second flag - and into buf; the last CTA raises the
+//                   rank's "slice reduced" flag in every rank's flag array.
+//   all-gather:     waits for every rank's second flag, copies slice q from rank q's buffer into buf.
+// Every element is summed by exactly one rank, in rank order, so all ranks again hold bit-identical results.
+template <typename T>
+__device__ __forceinline__ void store_vec(T* buf, int64_t i_vec, const T (&v)[16 / sizeof(T)], bool vec_ok) {
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) Pack { T v[VEC]; };
+    if (vec_ok) {
+        Pack p;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) p.v[k] = v[k];
+        reinterpret_cast<Pack*>(buf)[i_vec] = p;
+    } else {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) buf[i_vec * VEC + k] = v[k];
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(512) allreduce_reduce_scatter_kernel(T* __restrict__ buf, int64_t count, PeerTable peers, int n_ranks,
+                                                                       int rank, unsigned long long epoch) {
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) Pack { T v[VEC]; };
+    const size_t data_off = kFlagsBytes + (size_t)(epoch & 1ull) * kP2pCapacity;
+    const int64_t n_vec = count / VEC, per = (n_vec + n_ranks - 1) / n_ranks;
+    const int64_t lo = (int64_t)rank * per, hi = lo + per < n_vec ? lo + per : n_vec;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(buf) % 16) == 0;
+    if (threadIdx.x < n_ranks) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(peers.base[rank] + (size_t)threadIdx.x * 128);
+        while (ld_acquire_sys(f) < epoch) {}
+    }
+    __syncthreads();
+    Pack* own = reinterpret_cast<Pack*>(peers.base[rank] + data_off);
+    for (int64_t i = lo + first; i < hi; i += stride) {
+        T acc[VEC];
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) acc[k] = T(0);
+        for (int r = 0; r < n_ranks; ++r) {
+            const Pack p = reinterpret_cast<const Pack*>(peers.base[r] + data_off)[i];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) acc[k] += p.v[k];
+        }
+        Pack o;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) o.v[k] = acc[k];
+        own[i] = o;
+        store_vec<T>(buf, i, acc, vec_ok);
+    }
+    for (int64_t i = n_vec * VEC + first; i < count; i += stride) {          // fewer than VEC trailing elements: every rank sums them
+        T acc = T(0);
+        for (int r = 0; r < n_ranks; ++r) acc += reinterpret_cast<const T*>(peers.base[r] + data_off)[i];
+        buf[i] = acc;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int* counter = reinterpret_cast<unsigned int*>(peers.base[rank] + kCounter2Offset);
+        if (atomicAdd(counter, 1u) == gridDim.x - 1) {          // this rank's slice is complete
+            *counter = 0u;
+            __threadfence_system();
+            for (int r = 0; r < n_ranks; ++r)
+                st_release_sys(reinterpret_cast<unsigned long long*>(peers.base[r] + kFlagsBOffset + (size_t)rank * 128), epoch);
+        }
+    }
+}
+template <typename T>
+__global__ void __launch_bounds__(512) allreduce_all_gather_kernel(T* __restrict__ buf, int64_t count, PeerTable peers, int n_ranks, int rank,
+                                                                   unsigned long long epoch) {
+    constexpr int VEC = 16 / sizeof(T);
+    struct alignas(16) Pack { T v[VEC]; };
+    const size_t data_off = kFlagsBytes + (size_t)(epoch & 1ull) * kP2pCapacity;
+    const int64_t n_vec = count / VEC, per = (n_vec + n_ranks - 1) / n_ranks;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool vec_ok = (reinterpret_cast<uintptr_t>(buf) % 16) == 0;
+    if (threadIdx.x < n_ranks) {
+        const unsigned long long* f = reinterpret_cast<const unsigned long long*>(peers.base[rank] + kFlagsBOffset + (size_t)threadIdx.x * 128);
+        while (ld_acquire_sys(f) < epoch) {}
+    }
+    __syncthreads();
+    for (int q = 0; q < n_ranks; ++q) {
+        if (q == rank) continue;
+        const int64_t lo = (int64_t)q * per, hi = lo + per < n_vec ? lo + per : n_vec;
+        const Pack* __restrict__ src = reinterpret_cast<const Pack*>(peers.base[q] + data_off);
+        for (int64_t i = lo + first; i < hi; i += stride) {
+            const Pack p = src[i];
+            T v[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) v[k] = p.v[k];
+            store_vec<T>(buf, i, v, vec_ok);
+        }
+    }
+}
+
 // Symmetric buffers + IPC handle exchange (through NCCL, on the current device).  Any failure leaves the NCCL path.
 static void p2p_setup(Comm* c) {
     NcclApi& api = nccl_api();
@@ -252,7 +355,18 @@ static int allreduce(dpr_comm_t comm, T* buf, int64_t count, ncclDataType_t dt, 
             LaunchScope scope("allreduce_p2p_publish", s);
             allreduce_publish_kernel<T><<<(unsigned)ctas, 512, 0, s>>>(buf, count, c->peers, c->n_ranks, c->rank, c->epoch);
         }
-        {
+        // (the choice depends on the payload size and the rank count only: every rank takes the same path)
+        const bool two_shot = c->n_ranks >= 4 && (size_t)count * sizeof(T) * (size_t)(c->n_ranks - 1) >= kTwoShotPeerBytes;
+        if (two_shot) {
+            {
+                LaunchScope scope("allreduce_p2p_reduce_scatter", s);
+                allreduce_reduce_scatter_kernel<T><<<(unsigned)ctas, 512, 0, s>>>(buf, count, c->peers, c->n_ranks, c->rank, c->epoch);
+            }
+            {
+                LaunchScope scope("allreduce_p2p_all_gather", s);
+                allreduce_all_gather_kernel<T><<<(unsigned)ctas, 512, 0, s>>>(buf, count, c->peers, c->n_ranks, c->rank, c->epoch);
+            }
+        } else {
             LaunchScope scope("allreduce_p2p_reduce", s);
             allreduce_reduce_kernel<T><<<(unsigned)ctas, 512, 0, s>>>(buf, count, c->peers, c->n_ranks, c->rank, c->epoch);
         }

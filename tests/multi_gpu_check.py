@@ -34,11 +34,16 @@ assert torch.all(t == sum(range(1, world + 1))), "dpr_comm_allreduce_sum_f32 wro
 # types, a payload above the peer-memory capacity (NCCL path), and 60 calls back to back (the two symmetric buffers
 # alternate, a rank may be a call ahead of its peers)
 gen = torch.Generator(device=dev).manual_seed(100 + rank)
-for dtype, n in ((torch.float32, 400_003), (torch.float32, 4 * 1_000_000), (torch.float64, 300_001), (torch.float32, 5_000_000)):
-    x = torch.randn(n, generator=gen, device=dev, dtype=dtype)
+# (16 MB on >= 4 ranks takes the two-shot kernels - reduce-scatter + all-gather; `off` = 1 gives a buffer that is not
+# 16-byte aligned)
+for dtype, n, off in ((torch.float32, 400_003, 0), (torch.float32, 4 * 1_000_000, 0), (torch.float64, 300_001, 0),
+                      (torch.float32, 5_000_000, 0), (torch.float64, 2_000_000, 0), (torch.float32, 3_999_998, 1),
+                      (torch.float64, 1_999_999, 1)):
+    x = torch.randn(n + off, generator=gen, device=dev, dtype=dtype)[off:]
     want = x.clone()
     dist.all_reduce(want)
-    got = x.clone()
+    got = torch.empty(n + off, device=dev, dtype=dtype)[off:]
+    got.copy_(x)
     comm.all_reduce_(got)
     torch.cuda.synchronize()
     assert rel_l2(got.cpu().numpy(), want.cpu().numpy()) < (1e-6 if dtype == torch.float32 else 1e-14), (dtype, n)
