@@ -319,6 +319,7 @@ class Workload:
         step_bytes = (fwd_bytes if self.do_fwd else 0) + bwd_bytes
         roofline = dict(bound="hbm", kernel=dom, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=traffic,
                         algorithmic_bytes_per_launch=bytes_per_launch, kernel_ms=kernel_launch_ms[dom],
+                        kernel_ms_median=sorted(kernels[dom])[len(kernels[dom]) // 2],
                         launches_per_step=launches_per_step[dom], peak_source=peak_src,
                         whole_step=dict(algorithmic_bytes=step_bytes, achieved=step_bytes / (ms_per_step * 1e-3) / 1e9,
                                         frac=step_bytes / (ms_per_step * 1e-3) / 1e9 / peak))
