@@ -11,7 +11,7 @@ for cfg in cfg2 cfg3 cfg5; do
   timeout 200 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_${tag}_$cfg.csv python bench.py --config $cfg --steps 2 --warmup 3 --no-e2e --no-cpu --no-others > gpurun_out/ncu_launch_${tag}_$cfg.log 2>&1
 done
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:"fwd_tile2d_radial|pullback_gather2d" -c 2 -o gpurun_out/prof_${tag}_cfg2 -f python bench.py --config cfg2 --steps 1 --warmup 1 --no-e2e --no-cpu --no-others > gpurun_out/ncu_full_${tag}_cfg2.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:"fwd_tile3d|pullback_tile3d|tile_count|tile_scatter|sort_scatter4|hash_inputs|unpermute" -c 9 -o gpurun_out/prof_${tag}_cfg3 -f python bench.py --config cfg3 --steps 1 --warmup 1 --no-e2e --no-cpu --no-others > gpurun_out/ncu_full_${tag}_cfg3.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:"fwd_tile3d|pullback_tile3d|tile_count|tile_scatter|sort_scatter4|hash_inputs|unpermute" -c 11 -o gpurun_out/prof_${tag}_cfg3 -f python bench.py --config cfg3 --steps 1 --warmup 1 --no-e2e --no-cpu --no-others > gpurun_out/ncu_full_${tag}_cfg3.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:"pullback_tma2d" -c 1 -o gpurun_out/prof_${tag}_cfg5 -f python bench.py --config cfg5 --steps 1 --warmup 1 --no-e2e --no-cpu --no-others > gpurun_out/ncu_full_${tag}_cfg5.log 2>&1
 python - <<PY
 import json
