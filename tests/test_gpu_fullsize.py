@@ -170,3 +170,33 @@ def test_full_size_config4_pose_subset():
     ref = oracle.raster_pullback(np.asfortranarray(ds.cpu().numpy()), pts, rot, tr, bg, ow, pw, dtype=np.float32, n_slabs=8, f64_accumulate=True)
     for k in ("points", "rotation", "translation", "background", "out_weight", "point_weight"):
         assert rel_l2(getattr(pb, k).cpu().numpy(), getattr(ref, k)) <= 1e-5, k
+
+
+def test_tile3d_pose_groups():
+    """The 3-d tile path bins at most 2^27 (point, pose) pairs per pass: 2^21 points x 70 poses run as two pose groups
+    (64 + 6) that share the entry buffer - no bins can be cached, every group is binned again by the pullback.  Poses on both
+    sides of the group boundary against the oracle, and the pose-summed gradients of the whole batch."""
+    from tests.gpu_util import forced
+    n_in, P, B, grid = 3, (1 << 21) + 5, 70, (64, 32, 48)
+    rng = np.random.Generator(np.random.PCG64(5005))
+    pts = np.asfortranarray((0.4 * rng.standard_normal((n_in, P))).astype(np.float32))
+    rot = random_rotations(rng, 3, 3, B, np.float32)
+    tr = np.asfortranarray((0.1 * rng.standard_normal((3, B))).astype(np.float32))
+    ow = (0.5 + rng.random(B)).astype(np.float32)
+    d = [_dev(a) for a in (pts, rot, tr, None, ow, None)]
+    gen = torch.Generator(device="cuda").manual_seed(12)
+    ds = dpr_b200.empty_f(grid + (B,), torch.float32, "cuda")
+    ds.normal_(generator=gen)
+    with forced(forward_algo=3, pullback_algo=7, binning_cache=1):
+        out = dpr_b200.raster(grid, *d)
+        assert dpr_b200.last_path(0).startswith("tile3d_binned")
+        pb = dpr_b200.raster_pullback_(ds, *d)
+        assert dpr_b200.last_path(1).startswith("tile3d_binned")
+    sel = np.array([0, 63, 64, 69])
+    sub = lambda a: np.asfortranarray(a[..., sel])
+    ref_out = oracle.raster(grid, pts, sub(rot), sub(tr), None, ow[sel], None, dtype=np.float32, n_threads=4, f64_accumulate=True)
+    assert rel_l2(out[..., torch.from_numpy(sel).cuda()].cpu().numpy(), ref_out) <= 1e-5
+    ref = oracle.raster_pullback(np.asfortranarray(ds.cpu().numpy()), pts, rot, tr, None, ow, None, dtype=np.float32, n_slabs=8,
+                                 f64_accumulate=True)
+    for k in ("points", "rotation", "translation", "background", "out_weight", "point_weight"):
+        assert rel_l2(getattr(pb, k).cpu().numpy(), getattr(ref, k)) <= 1e-5, k
