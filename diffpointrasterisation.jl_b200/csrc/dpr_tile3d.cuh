@@ -609,13 +609,20 @@ fwd_tile3d_kernel(const Pt4<T>* __restrict__ pts4, const uint32_t* __restrict__ 
         const uint32_t tile_s = smem_u32(tile);
         // kBatch entries, then their kBatch points, are in flight at once: two dependent round trips per batch instead of
         // two per entry (an item has about four entries per thread, so a rolling prefetch never reaches steady state)
-        for (uint32_t e0 = threadIdx.x; e0 < total; e0 += kBatch * kThreads) {
-            uint32_t idx[kBatch];
+        uint32_t idx[kBatch], idx_next[kBatch];
 #pragma unroll
-            for (int j = 0; j < kBatch; ++j) idx[j] = e0 + j * kThreads < total ? cur.fetch(e0 + j * kThreads) : 0u;
+        for (int j = 0; j < kBatch; ++j) idx_next[j] = threadIdx.x + j * kThreads < total ? cur.fetch(threadIdx.x + j * kThreads) : 0u;
+        for (uint32_t e0 = threadIdx.x; e0 < total; e0 += kBatch * kThreads) {
+#pragma unroll
+            for (int j = 0; j < kBatch; ++j) idx[j] = idx_next[j];
             Pt4<T> qb[kBatch];
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) qb[j] = pts4[idx[j]];
+            if (e0 + kBatch * kThreads < total) {       // the next batch's entries travel while this batch is computed
+#pragma unroll
+                for (int j = 0; j < kBatch; ++j)
+                    idx_next[j] = e0 + (kBatch + j) * kThreads < total ? cur.fetch(e0 + (kBatch + j) * kThreads) : 0u;
+            }
 #pragma unroll
             for (int j = 0; j < kBatch; ++j) {
             const uint32_t e = e0 + j * kThreads;
@@ -821,19 +828,23 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
         return;
     }
 
-    // the first entry / point of this thread take off before the tile is waited for.  (Rolling prefetch, one entry and one
-    // point ahead: loading kBatch entries and points at once, as the forward does, leaves the memory pipe idle while the
-    // batch is computed and cost 27 us on config 3 - the TMA wait already hides the first round trips here.)
+    // the first entries / points of this thread take off before the tile is waited for.  (Rolling prefetch, two points and
+    // three entries ahead: loading kBatch entries and points at once, as the forward does, leaves the memory pipe idle while
+    // the batch is computed and cost 27 us on config 3 - the TMA wait already hides the first round trips here.)
     EntryCursor cur;
     uint32_t e = threadIdx.x;
     uint32_t idx = 0, idx_n = 0;
     Pt4<T> qn;
     qn.x = qn.y = qn.z = qn.w = T(0);
+    uint32_t idx_nn = 0;
+    Pt4<T> qnn = qn;
     if (e < total) {
         cur.init(&tab, entries);
         idx = cur.fetch(e);
         if (e + kThreads < total) idx_n = cur.fetch(e + kThreads);
+        if (e + 2 * kThreads < total) idx_nn = cur.fetch(e + 2 * kThreads);
         qn = pts4[idx];
+        if (e + kThreads < total) qnn = pts4[idx_n];
     }
     if (USE_TMA) mbar_wait(&bar, 0);
 
@@ -868,8 +879,10 @@ pullback_tile3d_kernel(const __grid_constant__ CUtensorMap map, const T* __restr
         const Pt4<T> q = qn;
         const uint32_t idx_c = idx;
         idx = idx_n;
-        if (e + kThreads < total) qn = pts4[idx];
-        if (e + 2 * kThreads < total) idx_n = cur.fetch(e + 2 * kThreads);
+        qn = qnn;                                       // two points in flight per thread
+        idx_n = idx_nn;
+        if (e + 2 * kThreads < total) qnn = pts4[idx_n];
+        if (e + 3 * kThreads < total) idx_nn = cur.fetch(e + 3 * kThreads);
         T x[N_IN];
         load_xyz<T, N_IN>(x, q);
         int i0[3];
