@@ -319,20 +319,27 @@ static __global__ void __launch_bounds__(256) tile_scatter_kernel(int P, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 5. the tile kernels: one CTA per (pose, tile) work item, 256 threads, at most ~50 (forward) / 64 (pullback) registers so
-// that five / four CTAs share an SM and the hardware scheduler overlaps their phases (range look-up, entry gathers,
-// accumulation, flush).
+// 5. the tile kernels: one CTA per (pose, tile) work item, 256 threads, 32 x 32 x 16 cells = 64 KB of Float32 per tile, so
+// that three CTAs share an SM (78 / 77 registers) and the hardware scheduler overlaps their phases (sub-list table, entry
+// and point gathers, accumulation, flush).
 //
-// What was measured on config 3 before settling here (profiles/ncu_r02_*_cfg3_summary.txt; all on the same B200 pool):
+// What was measured on config 3 on the way here (all on the same B200 pool):
 //   v2  CTA per item, float CAS atomics, div/mod in the flush        fwd 467 us (273 M warp instructions, issue 51 %)
 //   v2b + fixed-point atomics                                          fwd 414 us (324 M, issue 68 %, 39 warps / SM)
 //   v3  persistent CTAs, warp 0 does the bookkeeping between barriers  fwd 421 us, pullback 498 us (barrier stalls 32 %)
 //   v5  warp-specialised persistent CTAs (metadata producer warp, TMA  fwd 535 us, pullback 464 us: 190 M / 150 M
 //       producer warp, mbarrier rings, cross-item look-ahead)          instructions but 72 - 93 registers -> 20 - 27 warps
-//                                                                      per SM, issue 39 %: latency bound; forcing 56 - 64
-//                                                                      registers (spills) made it 675 / 889 us
+//                                                                      per SM, issue 39 %; forcing 56 - 64 registers
+//                                                                      (spills) made it 675 / 889 us
+//   v6  (this file) one CTA per item with the lean pieces              fwd 341 us, pullback 308 us
 // The instruction-lean pieces of v3 - v5 (division-free cell map, compact sub-list table, fixed-point accumulation,
 // factorised trilinear gradient, tensor-map TMA tile loads) are kept; the bookkeeping went back to the hardware.
+// With no points at all the kernels run at the HBM floor of their one pass over the volume (163 / 177 us for 1.07 GB);
+// every million points (16.8 M entries) adds 155 / 161 us that do not overlap with that pass: the entries are bound by
+// issue slots and the shared-memory pipe, not by load latency (deeper prefetching changes nothing), and three CTAs per SM,
+// each in one phase at a time, overlap the phases only statistically (tools/exp_tile3d_scaling.py).
+// The DPR_T3_* macros exist for tools/build_variants.py (experiment builds with other tile shapes); the defaults are the
+// product.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kMaxSlots = 27;
 
