@@ -235,6 +235,21 @@ def test_forward_radial_path(n_in, weights, opts):
     assert rel_l2(to_np(out)[:, :, keep], to_np(old)[:, :, keep]) <= 2e-6
 
 
+def test_forward_radial_single_pose_many_splits():
+    """One pose, 615 k points, point_sort forced: the radius-sorted kernel runs with ~296 point splits of ceil(601 / 296) = 3
+    chunks, so the last splits start beyond the last chunk and have no work - their prefetch must stay inside the padded copy
+    (the unclamped prefetch read 4.5 MB past the workspace in exactly this shape)."""
+    grid = (64, 64)
+    d = make_inputs(615, 3, 2, 615_000, 1, grid, np.float32)
+    out_ref, _ = _oracle_pair(d, grid, np.float32)
+    with forced(forward_algo=2, point_sort=1):
+        out = dpr_b200.raster(grid, *dev_args(d, np.float32))
+        path = dpr_b200.last_path(0)
+    assert "radial" in path, path
+    torch.cuda.synchronize()
+    assert rel_l2(to_np(out), out_ref) <= 1e-5, path
+
+
 def test_forward_radial_randomised_and_non_finite_poses():
     """Random shapes through the radius-sorted kernel (odd grid extents, P just above its threshold and not a multiple
     of the chunk length, few and many poses, sliced buffers), plus poses with NaN / Inf entries: those may produce
