@@ -142,7 +142,11 @@ int dpr_host_release(void);                    /* frees the staging arena of the
  * d_points (src/raster_pullback.jl:141) and d_point_weight (:146), which callers keep in one packed (N_in+1)*P buffer.
  * Rank 0 creates a 128-byte id (ncclUniqueId), ships it to the other ranks by any means, every rank calls
  * dpr_comm_init_rank, then dpr_comm_allreduce_sum_* after its local dpr_raster_pullback_* on the same stream.
- * NCCL is loaded with dlopen at first use; DPR_ERR_NCCL if it is not available. */
+ * NCCL is loaded with dlopen at first use; DPR_ERR_NCCL if it is not available.
+ * Payloads up to 16 MB are summed by the library's own kernels over peer memory (symmetric buffers mapped with CUDA IPC
+ * by dpr_comm_init_rank; flags written over NVLink; one-shot, or reduce-scatter + all-gather for large payloads on four or
+ * more ranks; every element is added in rank order, so all ranks receive bit-identical sums); larger payloads, and boxes
+ * without peer access, go through ncclAllReduce.  The calls are collective: every rank makes them in the same order. */
 typedef struct dpr_comm* dpr_comm_t;
 int dpr_comm_unique_id(void* id128);
 int dpr_comm_init_rank(dpr_comm_t* comm, int n_ranks, int rank, const void* id128);
