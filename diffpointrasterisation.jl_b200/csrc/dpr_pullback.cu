@@ -519,8 +519,10 @@ static int pullback_gather2d(const PullbackArgs<T>& a, const DeviceInfo& dev) {
 
 // Float32 images that fit a 2- or 3-stage shared-memory ring: TMA-staged kernel (dpr_pullback_tma.cuh).
 // `padded`: rows are fetched through a tensor map whose box is 4 columns wider than the image (bank-skewed pitch).
-static bool tma2d_can_pad(const int64_t* grid) { return (grid[0] % 4) == 0 && grid[0] + 4 <= 256 && grid[1] <= 256; }
-static int64_t tma2d_stage_words(const int64_t* grid, bool padded) { return (padded ? grid[0] + 4 : grid[0]) * grid[1]; }
+// padded: the staged image sits in a frame of zeros - 4 columns in front of every row, rows -2, -1, g1, g1 + 1, 4 guard words
+// (dpr_pullback_tma.cuh)
+static bool tma2d_can_pad(const int64_t* grid) { return (grid[0] % 4) == 0 && grid[0] + 4 <= 256 && grid[1] + 4 <= 256; }
+static int64_t tma2d_stage_words(const int64_t* grid, bool padded) { return padded ? (grid[0] + 4) * (grid[1] + 4) + 4 : grid[0] * grid[1]; }
 
 template <int N_IN>
 static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, int stages, bool padded) {
@@ -537,7 +539,7 @@ static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, i
     if (padded) {
         const cuuint64_t dims[3] = {(cuuint64_t)a.grid[0], (cuuint64_t)a.grid[1], (cuuint64_t)a.B};
         const cuuint64_t strides[2] = {(cuuint64_t)a.grid[0] * 4, (cuuint64_t)grid.cells * 4};
-        const cuuint32_t box[3] = {(cuuint32_t)(a.grid[0] + 4), (cuuint32_t)a.grid[1], 1u};
+        const cuuint32_t box[3] = {(cuuint32_t)(a.grid[0] + 4), (cuuint32_t)(a.grid[1] + 4), 1u};      // starts at (-4, -2)
         const cuuint32_t es[3] = {1u, 1u, 1u};
         EncodeTiledFn enc = tensor_map_encoder();
         if (!enc || enc(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(a.ds_dout), dims, strides, box, es,

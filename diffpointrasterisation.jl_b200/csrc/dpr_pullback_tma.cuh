@@ -27,7 +27,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // pitch of g0 + 4 words.  With the dense pitch (a multiple of the 32 banks) the bank of a cell depends on its column
 // only, and spatially sorted lanes - a blob ~10 pixels wide under every pose - serialised 5.3 ways per LDS (66 % of the
 // kernel's shared-memory wavefronts were bank conflicts, profiles/ncu_full_r01_v10_cfg5_summary.csv); with the padded pitch
-// the bank is (x + 4 y) mod 32.  The consumers' address arithmetic is unchanged apart from the pitch.
+// the bank is (x + 4 y) mod 32.
+// The box also starts four columns LEFT of the image and two rows ABOVE it and ends two rows below: the staged image sits in
+// a frame of zeros - (row r, column c) is word (r + 2) * pitch + c + 4, columns g0 and g0 + 1 of a row are the zero padding in
+// front of the next row (four guard words, zeroed once, follow the last row) - so the consumers clamp the lower-corner cell
+// into [-2, g] and load all four corners WITHOUT bounds predicates (src/raster_pullback.jl:51 skips out-of-bounds corners;
+// here they read zeros): 13 instructions per splat instead of 18 (config 5: 5.68 -> 5.48 ms).
 // !PADDED: 1-d bulk copy of the dense image (cp.async.bulk, UBLKCP), for rows that are not multiples of 16 bytes.
 template <int N_IN, int K, bool HAS_PW, int STAGES, bool PADDED>
 __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
@@ -42,9 +47,9 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int pitch = PADDED ? grid.g[0] + 4 : grid.g[0];            // words per staged row
     const int cells = (int)grid.cells;
-    const int stage_words = pitch * grid.g[1];
-    const uint32_t img_bytes = (uint32_t)stage_words * 4u;           // bytes one copy delivers (zero-filled columns included)
-    const size_t stage_stride = ((size_t)img_bytes + 127) / 128 * 128;
+    const int stage_words = pitch * (PADDED ? grid.g[1] + 4 : grid.g[1]);     // PADDED: rows -2 .. g1 + 1
+    const uint32_t img_bytes = (uint32_t)stage_words * 4u;           // bytes one copy delivers (zero-filled frame included)
+    const size_t stage_stride = ((size_t)img_bytes + (PADDED ? 16 : 0) + 127) / 128 * 128;      // as tma_pullback_smem()
     float* tiles = reinterpret_cast<float*>(smem_raw);
     unsigned char* after = smem_raw + stage_stride * STAGES;
     float* pose_par = reinterpret_cast<float*>(after);                 // [kTmaRound][PP]
@@ -66,6 +71,10 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
             mbar_init(&empty[s], kTmaConsumers / 32 + 1);
         }
         mbar_fence_init();
+        if constexpr (PADDED) {          // guard words behind each stage's last row (read as columns g0, g0 + 1 of row g1 + 1)
+            for (int s = 0; s < STAGES; ++s)
+                for (int w = 0; w < 4; ++w) reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s)[stage_words + w] = 0.f;
+        }
     }
     __syncthreads();
 
@@ -78,7 +87,7 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
             if constexpr (PADDED) {
                 asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
                                  smem_u32(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s)),
-                             "l"(&map), "r"(0), "r"(0), "r"((int)(b0 + i)), "r"(smem_u32(&full[s]))
+                             "l"(&map), "r"(-4), "r"(-2), "r"((int)(b0 + i)), "r"(smem_u32(&full[s]))
                              : "memory");
             } else {
                 tma_load_1d(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s, ds_dout + (b0 + i) * (int64_t)cells,
@@ -169,6 +178,7 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
             const float ows[2] = {ow * scale[0], ow * scale[1]};
             const float* __restrict__ tile = reinterpret_cast<const float*>(reinterpret_cast<unsigned char*>(tiles) + stage_stride * s);
             mbar_wait(&full[s], (i / STAGES) & 1);
+            const float* __restrict__ frame = tile + (2 * pitch + 4);   // PADDED: cell (0, 0) of the framed image
 
             float acc[8], acc_ow = 0.f;
 #pragma unroll
@@ -179,14 +189,28 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
                 float dl[2];
                 stencil2<float, N_IN>(x[k], R, neg_origin, scale, g, ix, iy, dl);
                 const bool valid = (valid_mask >> k) & 1u;
-                const bool x_lo = valid && (unsigned)ix < (unsigned)g[0], x_hi = valid && (unsigned)(ix + 1) < (unsigned)g[0];
-                const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
-                const int off = iy * pitch + ix;
                 float G00 = 0.f, G10 = 0.f, G01 = 0.f, G11 = 0.f;
-                if (x_lo && y_lo) G00 = tile[off];
-                if (x_hi && y_lo) G10 = tile[off + 1];
-                if (x_lo && y_hi) G01 = tile[off + pitch];
-                if (x_hi && y_hi) G11 = tile[off + pitch + 1];
+                if constexpr (PADDED) {
+                    // clamp into the frame of zeros (at -2 both corners of a dimension are outside the image); padding lanes
+                    // (p >= P) are sent to the zero columns
+                    int cx = ix < -2 ? -2 : ix, cy = iy < -2 ? -2 : iy;
+                    cx = cx > g[0] ? g[0] : cx;
+                    cy = cy > g[1] ? g[1] : cy;
+                    if (!valid) cx = g[0];
+                    const float* __restrict__ c00 = frame + (cy * pitch + cx);
+                    G00 = c00[0];
+                    G10 = c00[1];
+                    G01 = c00[pitch];
+                    G11 = c00[pitch + 1];
+                } else {
+                    const bool x_lo = valid && (unsigned)ix < (unsigned)g[0], x_hi = valid && (unsigned)(ix + 1) < (unsigned)g[0];
+                    const bool y_lo = (unsigned)iy < (unsigned)g[1], y_hi = (unsigned)(iy + 1) < (unsigned)g[1];
+                    const int off = iy * pitch + ix;
+                    if (x_lo && y_lo) G00 = tile[off];
+                    if (x_hi && y_lo) G10 = tile[off + 1];
+                    if (x_lo && y_hi) G01 = tile[off + pitch];
+                    if (x_hi && y_hi) G11 = tile[off + pitch + 1];
+                }
                 float s_, gx, gy;
                 bilinear_with_gradient(G00, G10, G01, G11, dl[0], dl[1], s_, gx, gy);
                 acc_ow += HAS_PW ? s_ * pw[k] : s_;
@@ -238,7 +262,7 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
     }
 }
 
-// `cells`: words one stage holds - g0 * g1 (dense) or (g0 + 4) * g1 (padded)
+// `cells`: words one stage holds - g0 * g1 (dense) or (g0 + 4) * (g1 + 4) + 4 guard words (padded)
 inline size_t tma_pullback_smem(int64_t cells, int stages, int n_in) {
     const int NV = 2 * n_in + 3, PP = (NV + 3) / 4 * 4;
     const size_t stage_stride = ((size_t)cells * 4 + 127) / 128 * 128;
