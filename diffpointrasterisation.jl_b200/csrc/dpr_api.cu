@@ -212,6 +212,7 @@ static int arena_get(int dev, int op, HostArena*& out) {
         for (int i = 0; i < NSTREAM && e == cudaSuccess; ++i) e = cudaStreamCreateWithFlags(&a.streams[i], cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&a.shared_ready, cudaEventDisableTiming);
         for (int i = 0; i < NSTREAM && e == cudaSuccess; ++i) e = cudaMalloc(&a.ws[i], 4096);
+        for (int i = 0; i < NSTREAM && e == cudaSuccess; ++i) e = cudaMemset(a.ws[i], 0, 256);      // clean binning-cache header
         if (e != cudaSuccess) {
             for (int i = 0; i < NSTREAM; ++i) {
                 if (a.streams[i]) cudaStreamDestroy(a.streams[i]);
@@ -589,7 +590,9 @@ int dpr_host_release(void) {
         a.slot_bytes = 0;
         for (int i = 0; i < NSTREAM; ++i) { if (a.ws[i]) cudaFree(a.ws[i]); a.ws[i] = nullptr; }
         a.ws_bytes = 0;
-        for (int i = 0; i < NSTREAM; ++i) { if (cudaMalloc(&a.ws[i], 4096) != cudaSuccess) return DPR_ERR_CUDA; }
+        for (int i = 0; i < NSTREAM; ++i) {
+            if (cudaMalloc(&a.ws[i], 4096) != cudaSuccess || cudaMemset(a.ws[i], 0, 256) != cudaSuccess) return DPR_ERR_CUDA;
+        }
         a.ws_bytes = 4096;
         if (a.shared) cudaFree(a.shared);
         a.shared = nullptr; a.shared_bytes = 0;
