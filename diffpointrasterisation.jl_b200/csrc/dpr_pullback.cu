@@ -525,7 +525,7 @@ static bool tma2d_can_pad(const int64_t* grid) { return (grid[0] % 4) == 0 && gr
 static int64_t tma2d_stage_words(const int64_t* grid, bool padded) { return padded ? (grid[0] + 4) * (grid[1] + 4) + 4 : grid[0] * grid[1]; }
 
 #ifndef DPR_TMA2D_K
-#define DPR_TMA2D_K 10         /* points a consumer thread owns (8: 5.47 ms, 10: 5.43 ms, 12: spills, 5.77 ms on config 5) */
+#define DPR_TMA2D_K 8          /* points a consumer thread owns (config 5: 8 -> 5.55 ms, 10 -> 5.65 ms, 12 spills) */
 #endif
 template <int N_IN>
 static int pullback_tma2d(const PullbackArgs<float>& a, const DeviceInfo& dev, int stages, bool padded) {

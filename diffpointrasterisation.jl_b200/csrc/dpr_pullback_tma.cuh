@@ -32,7 +32,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) {
 // a frame of zeros - (row r, column c) is word (r + 2) * pitch + c + 4, columns g0 and g0 + 1 of a row are the zero padding in
 // front of the next row (four guard words, zeroed once, follow the last row) - so the consumers clamp the lower-corner cell
 // into [-2, g] and load all four corners WITHOUT bounds predicates (src/raster_pullback.jl:51 skips out-of-bounds corners;
-// here they read zeros): 13 instructions per splat instead of 18 (config 5: 5.68 -> 5.48 ms).
+// here they read zeros): 13 instructions per splat instead of 18.
 // !PADDED: 1-d bulk copy of the dense image (cp.async.bulk, UBLKCP), for rows that are not multiples of 16 bytes.
 template <int N_IN, int K, bool HAS_PW, int STAGES, bool PADDED>
 __global__ void __launch_bounds__(kTmaConsumers + 32, 1)
@@ -115,7 +115,7 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
                 const float tot = warp_sum(acc0 + acc1);
                 if (lane == 0) d_background[b0 + i] = tot;      // src/raster_pullback.jl:78
             }
-            __syncwarp();
+            __syncwarp();           // (the store of the tile sum above depends on every lane's loads: they have returned)
             if (lane == 0) mbar_arrive(&empty[s]);
         }
         return;
@@ -224,8 +224,6 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
                     dpt[k][j] = fmaf(R[1][j], sy, fmaf(R[0][j], sx, dpt[k][j]));
                 }
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);          // this warp is done with the staged image
             if constexpr (N_IN == 2) acc[6] = acc_ow;
             butterfly8(acc, lane);
             if constexpr (N_IN == 3) acc_ow = warp_sum(acc_ow);
@@ -238,6 +236,18 @@ pullback_tma2d_kernel(const __grid_constant__ CUtensorMap map, const float* __re
                 }
                 if (mine) atomicAdd(&pose_acc[bl * NV + slot], val);
             }
+            // Release the stage HERE, not right after the gathers.  A warp issues in order and an instruction waits for its
+            // operands: the atomic above cannot issue before `val` - which depends, through the shuffles, on every load of
+            // every lane from the stage - is ready, so by now all of this warp's reads of the staged image have returned.
+            // An arrive straight after the point loop issues while the last loads are still in flight (SASS: LDS x 4,
+            // WARPSYNC, SYNCS.ARRIVE; their consumers are scheduled behind it), and the producer's next TMA copy into the
+            // stage then overwrote cells a late lane was about to read: a handful of wrong splats of one pose in one warp, in
+            // one run out of three on some shapes (tools/soak.py; tests/test_gpu_parity.py::
+            // test_pullback_tma2d_stage_release_is_ordered).  Measured alternatives on config 5 (10 points per thread):
+            // fence.acq_rel.cta in front of the arrive 5.92 ms, a volatile store of acc_ow in front of it 5.83 ms, this 5.66 ms
+            // (the racy release: 5.43 ms); with 8 points per thread this release runs at 5.55 ms.
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
         }
         named_bar_sync(1, kTmaConsumers);
         for (int i = threadIdx.x; i < n_round * NV; i += kTmaConsumers) {

@@ -960,6 +960,26 @@ def test_randomised_3d_shapes_tile_paths():
         assert dpr_b200.last_path(1) == "tile3d_binned_coop"
 
 
+def test_pullback_tma2d_stage_release_is_ordered():
+    """The TMA-staged 2-d pullback releases a ring stage to the producer only after its reads of the stage were performed.
+    Without the fence in front of the `empty` arrive, this shape (one pose chunk of 29 poses through the 3-stage ring, clouds
+    mostly outside the image) returned a handful of wrong splats of one pose in about one run out of three - found by
+    tools/soak.py, invisible to single runs."""
+    grid, P, B = (92, 87), 76669, 29
+    d = make_inputs(380995414, 3, 2, P, B, grid, np.float32, True)
+    d["translation"] *= 4.0
+    ref = oracle.raster_pullback(d["ds_dout"], *(d[k] for k in FIELDS), dtype=np.float32, f64_accumulate=True, n_slabs=8)
+    args = dev_args(d, np.float32)
+    ds = to_dev(d["ds_dout"], torch.float32)
+    for opts in (dict(pullback_algo=4), dict(pullback_algo=4, tile3d_tma=1)):
+        with forced(**opts):
+            for rep in range(25):
+                pb = dpr_b200.raster_pullback_(ds, *args)
+                assert dpr_b200.last_path(1).startswith("tma2d")
+                for k in FIELDS:
+                    assert rel_l2(to_np(getattr(pb, k)), getattr(ref, k)) <= 1e-5, (opts, rep, k)
+
+
 def test_multi_gpu_check_script():
     """tests/multi_gpu_check.py under torchrun on two GPUs: the library's NCCL all-reduce and the pose-sharded pullback
     against a single-GPU run.  Skipped on boxes with one GPU (the driver's -m gpu run); tools/run_r02_multi.sh runs it."""
